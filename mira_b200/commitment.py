@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's `CommitmentKey<C>` (/root/reference/src/commitment.rs:26-167)
+over the C ABI.  Same method names, argument meaning and error behaviour, so parity tests read like
+the reference's own: `CommitmentKey.commit(v)` == `ck.commit(&v)`.
+
+The reference is Rust; this image has no Rust toolchain, so this Python class (and the C++ header
+include/mira_commitment.hpp) stand where the Rust shim of INTEGRATION.md would.  All arithmetic is
+in libmira_b200.so (CUDA, sm_100a); nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from . import _native as N
+
+BN254_G1 = 0       # halo2curves::bn256::G1Affine
+GRUMPKIN_G1 = 1    # halo2curves::grumpkin::G1Affine
+SCALAR_BYTES = 32
+POINT_BYTES = 64
+IDENTITY = bytes(POINT_BYTES)   # CommitmentKey::default_value() == C::identity() == (0, 0)
+
+
+class TooLongInput(ValueError):
+    """commitment::Error::TooLongInput { input_len, limit } (src/commitment.rs:20-24)."""
+
+    def __init__(self, input_len: int, limit: int):
+        super().__init__(f"Can't commit too long input: input len: {input_len}, but limit is {limit}")
+        self.input_len = input_len
+        self.limit = limit
+
+
+class CudaError(RuntimeError):
+    """Any CUDA failure.  The reference has no such error path, so callers abort (no CPU fallback)."""
+
+
+class NotOnCurve(ValueError):
+    """io::ErrorKind::InvalidData "Wrong file in cache, some ptr out of curve" (src/commitment.rs:145-153)."""
+
+
+def _check(rc: int, n: int = 0, limit: int = 0):
+    if rc == N.MIRA_OK:
+        return
+    msg = N.last_error()
+    if rc == N.MIRA_ERR_TOO_LONG_INPUT:
+        raise TooLongInput(n, limit)
+    if rc == N.MIRA_ERR_NOT_ON_CURVE:
+        raise NotOnCurve(msg)
+    if rc == N.MIRA_ERR_INVALID:
+        raise ValueError(msg)
+    raise CudaError(msg)
+
+
+def _as_ptr(buf):
+    """bytes / bytearray / memoryview / numpy array / torch CPU tensor -> (address, nbytes, keepalive)."""
+    if hasattr(buf, "data_ptr"):          # torch tensor (CPU or CUDA)
+        return buf.data_ptr(), buf.numel() * buf.element_size(), buf
+    if hasattr(buf, "ctypes") and hasattr(buf, "nbytes"):   # numpy
+        return buf.ctypes.data, buf.nbytes, buf
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p).value, len(buf), buf
+    mv = memoryview(buf)
+    arr = (C.c_char * mv.nbytes).from_buffer(mv)
+    return C.addressof(arr), mv.nbytes, (arr, mv)
+
+
+class CommitmentKey:
+    """`CommitmentKey<C>`: an immutable vector of affine generators resident in GPU memory."""
+
+    def __init__(self, curve: int, bases, device: int = 0, on_device: bool = False, n: Optional[int] = None):
+        L = N.lib()
+        ptr, nbytes, keep = _as_ptr(bases) if bases is not None else (None, 0, None)
+        if n is None:
+            n = nbytes // POINT_BYTES
+        self.curve = curve
+        self.device = device
+        self._n = n
+        self._ctx = C.c_void_p()
+        _check(L.mira_msm_ctx_create(curve, ptr, n, 1 if on_device else 0, device, C.byref(self._ctx)))
+
+    # -- reference API -------------------------------------------------------------------------
+    @staticmethod
+    def default_value() -> bytes:
+        return IDENTITY
+
+    def len(self) -> int:
+        return int(N.lib().mira_msm_ctx_len(self._ctx))
+
+    __len__ = len
+
+    def is_empty(self) -> bool:
+        return self.len() == 0
+
+    def commit(self, v) -> bytes:
+        """`ck.commit(&v)`: v = n x 32 B Montgomery scalars in HOST memory -> 64 B affine point."""
+        ptr, nbytes, keep = _as_ptr(v)
+        n = nbytes // SCALAR_BYTES
+        out = C.create_string_buffer(POINT_BYTES)
+        _check(N.lib().mira_msm_commit(self._ctx, ptr, n, out), n, self._n)
+        return out.raw
+
+    @classmethod
+    def load_from_file(cls, file_path: str, k: int, curve: int, device: int = 0) -> "CommitmentKey":
+        """Raw memory-image key file, 64 * 2^k bytes (src/commitment.rs:109-124)."""
+        want = POINT_BYTES << k
+        with open(file_path, "rb") as f:
+            data = f.read(want)
+        if len(data) != want:
+            raise IOError(f"{file_path}: expected {want} bytes, got {len(data)}")   # read_exact failure
+        return cls(curve, data, device)
+
+    @classmethod
+    def load_or_setup_cache(cls, cache_folder: str, label: str, k: int, curve: int, device: int = 0,
+                            setup_seed: int = 0x4D495241) -> "CommitmentKey":
+        """{cache_folder}/{label}/{k}.bin if present (with the on-curve check, src/commitment.rs:134-156),
+        else generate, save and return a key (src/commitment.rs:157-166)."""
+        path = os.path.join(cache_folder, label, f"{k}.bin")
+        if os.path.exists(path):
+            key = cls.load_from_file(path, k, curve, device)
+            key.check_on_curve()
+            return key
+        key = cls.setup(k, label.encode(), curve, device, seed=setup_seed)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        key.save_to_file(path)
+        return key
+
+    @classmethod
+    def setup(cls, k: int, label: bytes, curve: int, device: int = 0, seed: int = 0x4D495241) -> "CommitmentKey":
+        """Deterministic synthetic key of 2^k points generated on the GPU.
+
+        NOT bit-compatible with the reference's `setup` (src/commitment.rs:52-76): that one hashes
+        Shake256(label) blocks to the curve with halo2curves' `hash_to_curve` (un-vendored) in
+        `par_bridge` order (unordered), so keys are only ever compared through their cached bytes
+        (SURVEY.md §3.4).  Use load_from_file / load_or_setup_cache for reference-made keys."""
+        assert k < 32
+        import torch
+        n = 1 << k
+        mix = seed ^ int.from_bytes(label[:8].ljust(8, b"\0"), "little")
+        buf = torch.empty(n * POINT_BYTES, dtype=torch.uint8, device=f"cuda:{device}")
+        _check(N.lib().mira_gen_bases(curve, mix & 0xFFFFFFFFFFFFFFFF, 0, n, device, buf.data_ptr()))
+        return cls(curve, buf, device, on_device=True)
+
+    def save_to_file(self, file_path: str):
+        raise NotImplementedError("keys are saved from the host copy; see CommitmentKey.setup / tests")
+
+    # -- extensions used by the GPU pipeline ------------------------------------------------------
+    def check_on_curve(self):
+        _check(N.lib().mira_msm_ctx_check_on_curve(self._ctx))
+
+    def prepare(self, n: int):
+        """Build the fixed-base table commits of length n use (otherwise built lazily on first commit)."""
+        _check(N.lib().mira_msm_ctx_prepare(self._ctx, n), n, self._n)
+
+    def commit_device(self, scalars_dev_ptr: int, n: int, stream: int = 0) -> bytes:
+        out = C.create_string_buffer(POINT_BYTES)
+        _check(N.lib().mira_msm_commit_device(self._ctx, scalars_dev_ptr, n, out, stream or None), n, self._n)
+        return out.raw
+
+    def partial(self, scalars, n: Optional[int] = None, on_device: bool = False, stream: int = 0) -> bytes:
+        """Un-normalised XYZZ partial sum (128 B) of this rank's slice."""
+        if on_device:
+            ptr = scalars
+        else:
+            ptr, nbytes, keep = _as_ptr(scalars)
+            n = nbytes // SCALAR_BYTES if n is None else n
+        out = C.create_string_buffer(128)
+        _check(N.lib().mira_msm_partial(self._ctx, ptr, n, 1 if on_device else 0, out, stream or None), n, self._n)
+        return out.raw
+
+    def stats(self) -> dict:
+        st = N.MsmStats()
+        _check(N.lib().mira_msm_get_stats(self._ctx, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def set_profiling(self, on: bool):
+        _check(N.lib().mira_msm_set_profiling(self._ctx, 1 if on else 0))
+
+    def set_window(self, c: int):
+        _check(N.lib().mira_msm_set_window(self._ctx, c))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            N.lib().mira_msm_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def combine_partials(curve: int, partials: bytes, device: int = 0) -> bytes:
+    """Fold 128-byte XYZZ partials (one per rank) into the normalised affine commitment."""
+    out = C.create_string_buffer(POINT_BYTES)
+    _check(N.lib().mira_msm_combine(curve, partials, len(partials) // 128, device, out))
+    return out.raw

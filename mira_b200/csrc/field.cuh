@@ -1,0 +1,163 @@
+// field.cuh — BN254 Fq / Fr arithmetic on 8 x 32-bit limbs, Montgomery form with R = 2^256.
+//
+// Replaces (device side) halo2curves' 4x64-limb `Fq` / `Fr` that the reference reaches through
+// halo2_proofs (src/lib.rs:24-27, src/commitment.rs:11).  Byte layout is identical: 32 bytes
+// little-endian of value*2^256 mod m, so reference buffers are used without conversion.
+//
+// The multiplier bodies are generated (tools/gen_field_ptx.py -> field_gen.cuh) as inline PTX
+// whose mad.lo.cc/madc.hi.cc pairs ptxas fuses into IMAD.WIDE.U32[.X]; modulus limbs are
+// immediates.  B200 measured issue rate for IMAD.WIDE.U32 is 32 lanes/clk/SM (profiles/
+// r01_intpipe_microbench.jsonl), which is the roofline denominator of every kernel built on this.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "field_gen.cuh"
+
+namespace mira {
+
+struct FqTag {};   // modulus p (BN254 base field;  Grumpkin scalar field)
+struct FrTag {};   // modulus r (BN254 scalar field; Grumpkin base field)
+
+template <class F> struct FieldParams;
+template <> struct FieldParams<FqTag> {
+  // p = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+  __host__ __device__ static constexpr uint32_t mod(int i) {
+    constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return v[i];
+  }
+  // R mod p  (Montgomery form of 1)
+  __host__ __device__ static constexpr uint32_t one(int i) {
+    constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return v[i];
+  }
+  // R^2 mod p
+  __host__ __device__ static constexpr uint32_t r2(int i) {
+    constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return v[i];
+  }
+};
+template <> struct FieldParams<FrTag> {
+  // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+  __host__ __device__ static constexpr uint32_t mod(int i) {
+    constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return v[i];
+  }
+  __host__ __device__ static constexpr uint32_t one(int i) {
+    constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return v[i];
+  }
+  __host__ __device__ static constexpr uint32_t r2(int i) {
+    constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return v[i];
+  }
+};
+
+// A field element in registers.  F selects the modulus at compile time.
+template <class F>
+struct Fe {
+  uint32_t v[8];
+};
+
+template <class F> __device__ __forceinline__ Fe<F> fe_zero() {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+  return r;
+}
+template <class F> __device__ __forceinline__ Fe<F> fe_one() {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = FieldParams<F>::one(i);
+  return r;
+}
+template <class F> __device__ __forceinline__ bool fe_is_zero(const Fe<F>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i];
+  return o == 0;
+}
+template <class F> __device__ __forceinline__ bool fe_eq(const Fe<F>& a, const Fe<F>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+// ---- dispatch onto the generated bodies ------------------------------------------------------
+__device__ __forceinline__ void mont_mul_raw(FqTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mont_mul_Fq(r, a, b); }
+__device__ __forceinline__ void mont_mul_raw(FrTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mont_mul_Fr(r, a, b); }
+__device__ __forceinline__ void mont_sqr_raw(FqTag, uint32_t (&r)[8], const uint32_t (&a)[8]) { gen::mont_sqr_Fq(r, a); }
+__device__ __forceinline__ void mont_sqr_raw(FrTag, uint32_t (&r)[8], const uint32_t (&a)[8]) { gen::mont_sqr_Fr(r, a); }
+__device__ __forceinline__ void mod_add_raw(FqTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mod_add_Fq(r, a, b); }
+__device__ __forceinline__ void mod_add_raw(FrTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mod_add_Fr(r, a, b); }
+__device__ __forceinline__ void mod_sub_raw(FqTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mod_sub_Fq(r, a, b); }
+__device__ __forceinline__ void mod_sub_raw(FrTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mod_sub_Fr(r, a, b); }
+
+template <class F> __device__ __forceinline__ Fe<F> fe_mul(const Fe<F>& a, const Fe<F>& b) {
+  Fe<F> r;
+  mont_mul_raw(F{}, r.v, a.v, b.v);
+  return r;
+}
+template <class F> __device__ __forceinline__ Fe<F> fe_sqr(const Fe<F>& a) {
+  Fe<F> r;
+  mont_sqr_raw(F{}, r.v, a.v);
+  return r;
+}
+template <class F> __device__ __forceinline__ Fe<F> fe_add(const Fe<F>& a, const Fe<F>& b) {
+  Fe<F> r;
+  mod_add_raw(F{}, r.v, a.v, b.v);
+  return r;
+}
+template <class F> __device__ __forceinline__ Fe<F> fe_sub(const Fe<F>& a, const Fe<F>& b) {
+  Fe<F> r;
+  mod_sub_raw(F{}, r.v, a.v, b.v);
+  return r;
+}
+template <class F> __device__ __forceinline__ Fe<F> fe_dbl(const Fe<F>& a) { return fe_add(a, a); }
+template <class F> __device__ __forceinline__ Fe<F> fe_neg(const Fe<F>& a) { return fe_sub(fe_zero<F>(), a); }
+
+// Montgomery -> canonical (PrimeField::to_repr): multiply by the raw integer 1.
+template <class F> __device__ __forceinline__ Fe<F> fe_to_canonical(const Fe<F>& a) {
+  Fe<F> one = fe_zero<F>();
+  one.v[0] = 1;
+  return fe_mul(a, one);
+}
+// canonical -> Montgomery
+template <class F> __device__ __forceinline__ Fe<F> fe_from_canonical(const Fe<F>& a) {
+  Fe<F> r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r2.v[i] = FieldParams<F>::r2(i);
+  return fe_mul(a, r2);
+}
+
+// a^(m-2) by square-and-multiply over the (compile-time) modulus bits.  0 -> 0.
+template <class F> __device__ __noinline__ Fe<F> fe_inv(const Fe<F>& a) {
+  Fe<F> acc = fe_one<F>();
+  // exponent = MOD - 2 (MOD is odd and its low word is > 2 for both fields)
+  for (int w = 7; w >= 0; w--) {
+    uint32_t e = FieldParams<F>::mod(w) - (w == 0 ? 2u : 0u);
+    for (int b = 31; b >= 0; b--) {
+      acc = fe_sqr(acc);
+      if ((e >> b) & 1u) acc = fe_mul(acc, a);
+    }
+  }
+  return acc;
+}
+
+// ---- 128-bit vectorised global-memory access (elements are 32-byte aligned in all our buffers)
+template <class F> __device__ __forceinline__ Fe<F> fe_load(const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = __ldg(q), hi = __ldg(q + 1);
+  Fe<F> r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+template <class F> __device__ __forceinline__ void fe_store(void* p, const Fe<F>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+}  // namespace mira

@@ -1,0 +1,324 @@
+// msm_kernels.cuh — device kernels of the fixed-base signed-window Pippenger MSM.
+//
+// Replaces halo2_proofs::arithmetic::best_multiexp as called from CommitmentKey::commit
+// (/root/reference/src/commitment.rs:78-87).  Pipeline:
+//   k_digits      scalar: Montgomery -> canonical, signed c-bit digits, (bucket, point-ref) pairs
+//   sort          group the n*W pairs by bucket
+//   k_accumulate  load-balanced segmented XYZZ mixed-add over the sorted list (fixed-size chunks)
+//   k_combine     stitch runs that straddle chunk boundaries
+//   k_reduce_*    S = sum_b b * bucket[b] by chunked running sums + tree sum
+//   k_finalize    to_affine
+// The key is static, so windows j > 0 use precomputed points 2^(c*j) * P_i (k_precompute) and ALL
+// windows share ONE bucket set: no per-window doublings, one reduction.
+#pragma once
+#include "curve.cuh"
+
+namespace mira {
+
+constexpr uint32_t REF_NEG = 0x80000000u;       // sign flag in a point reference
+constexpr uint32_t PK_OPEN_LEFT = 0x80000000u;  // partial continues a run from the previous chunk
+constexpr uint32_t PK_OPEN_RIGHT = 0x40000000u; // partial's run continues in the next chunk
+constexpr uint32_t PK_KEY_MASK = 0x3fffffffu;
+
+// ------------------------------------------------------------------ digits
+// One thread per scalar.  keys/refs are window-major (entry j*n + i) so warps write coalesced rows.
+// digit d_j in [-2^(c-1)+1, 2^(c-1)]; key = |d_j| (0 = nothing to add), ref = j*n_cover + i | sign.
+template <class SF>
+__global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars, uint32_t n, int c, int W,
+                                                uint32_t n_cover, uint32_t* __restrict__ keys,
+                                                uint32_t* __restrict__ refs, uint32_t* __restrict__ counts) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<SF> s = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + (size_t)i * 32));
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
+  uint32_t carry = 0;
+  for (int j = 0; j < W; j++) {
+    int bit = j * c;
+    int w = bit >> 5, sh = bit & 31;
+    uint32_t lo = (w < 8) ? s.v[w] : 0u;
+    uint32_t hi = (w + 1 < 8) ? s.v[w + 1] : 0u;
+    uint32_t d = (sh ? ((lo >> sh) | (hi << (32 - sh))) : lo) & mask;
+    d += carry;
+    uint32_t neg = 0;
+    carry = 0;
+    if (d > half) {           // d in (half, 2^c] -> d - 2^c in (-half, 0]
+      d = (1u << c) - d;
+      neg = (d != 0) ? REF_NEG : 0u;
+      carry = 1;
+    }
+    size_t e = (size_t)j * n + i;
+    keys[e] = d;
+    refs[e] = ((uint32_t)j * n_cover + i) | neg;
+    if (d) atomicAdd(&counts[d], 1u);
+  }
+}
+
+// ------------------------------------------------------------------ exclusive scan (3 phases)
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem, uint32_t& total) {
+  // smem: blockDim.x / 32 words
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    smem[lane] = w;   // inclusive warp totals (blockDim/32 <= 32)
+  }
+  __syncthreads();
+  uint32_t warp_off = warp ? smem[warp - 1] : 0u;
+  total = smem[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
+                                                                 uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t sm[32];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? in[base + k] : 0u;
+  uint32_t total;
+  block_exclusive_scan(s, sm, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: in-place exclusive scan of up to SCAN_TILE*... tile sums (looped)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(uint32_t* __restrict__ data, uint32_t n) {
+  __shared__ uint32_t sm[32];
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < n; base += SCAN_THREADS) {
+    uint32_t idx = base + threadIdx.x;
+    uint32_t v = (idx < n) ? data[idx] : 0u;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, sm, total);
+    if (idx < n) data[idx] = running + ex;
+    running += total;
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
+                                                             const uint32_t* __restrict__ tile_offsets,
+                                                             uint32_t* __restrict__ out) {
+  __shared__ uint32_t sm[32];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, sm, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+// ------------------------------------------------------------------ scatter (counting sort, v1)
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ refs,
+                                                 size_t n_entries, uint32_t* __restrict__ cursor,
+                                                 uint32_t* __restrict__ skeys, uint32_t* __restrict__ srefs) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  uint32_t k = keys[e];
+  if (k == 0) return;
+  uint32_t pos = atomicAdd(&cursor[k], 1u);
+  skeys[pos] = k;
+  srefs[pos] = refs[e];
+}
+
+// ------------------------------------------------------------------ accumulate
+// Sorted non-zero entries occupy [0, n_sorted).  Thread t owns entries [t*L, (t+1)*L): every thread
+// does the same number of mixed adds whatever the bucket-size distribution is.  A run (maximal
+// range of equal keys) that lies wholly inside one chunk is written straight to its bucket; a run
+// that touches a chunk edge and continues beyond it becomes a "partial" (slot 2t for the chunk's
+// first run, 2t+1 for its last) that k_combine stitches.
+template <class CF>
+__device__ __forceinline__ Affine<CF> load_ref(const void* __restrict__ table, uint32_t ref) {
+  Affine<CF> p = aff_load<CF>(reinterpret_cast<const char*>(table) + (size_t)(ref & ~REF_NEG) * 64);
+  if (ref & REF_NEG) {
+    if (!fe_is_zero(p.y)) p.y = fe_neg(p.y);
+  }
+  return p;
+}
+
+template <class CF>
+__global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ skeys,
+                                                    const uint32_t* __restrict__ srefs, uint32_t n_sorted, int L,
+                                                    const void* __restrict__ table, void* __restrict__ buckets,
+                                                    uint32_t* __restrict__ part_keys, void* __restrict__ part_pts) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  size_t begin = (size_t)t * L;
+  if (begin >= n_sorted) return;
+  size_t end = begin + L < n_sorted ? begin + L : n_sorted;
+  uint32_t prev_key = begin ? skeys[begin - 1] : 0u;
+  uint32_t next_key = end < n_sorted ? skeys[end] : 0u;
+  uint32_t cur = skeys[begin];
+  bool first = true;
+  uint32_t pk0 = 0, pk1 = 0;
+  Xyzz<CF> acc = xyzz_identity<CF>();
+  for (size_t e = begin; e < end; e++) {
+    uint32_t k = skeys[e];
+    if (k != cur) {
+      // the finished run ends strictly inside the chunk: it can only be open to the left
+      if (first && prev_key == cur) {
+        pk0 = cur | PK_OPEN_LEFT;
+        xyzz_store<CF>(reinterpret_cast<char*>(part_pts) + (size_t)(2 * t) * 128, acc);
+      } else {
+        xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)cur * 128, acc);
+      }
+      first = false;
+      cur = k;
+      acc = xyzz_identity<CF>();
+    }
+    Affine<CF> p = load_ref<CF>(table, srefs[e]);
+    xyzz_madd(acc, p);
+  }
+  {
+    bool open_left = first && prev_key == cur;
+    bool open_right = next_key == cur;
+    if (!open_left && !open_right) {
+      xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)cur * 128, acc);
+    } else {
+      uint32_t pk = cur | (open_left ? PK_OPEN_LEFT : 0u) | (open_right ? PK_OPEN_RIGHT : 0u);
+      int slot = first ? 0 : 1;
+      if (slot == 0) pk0 = pk; else pk1 = pk;
+      xyzz_store<CF>(reinterpret_cast<char*>(part_pts) + (size_t)(2 * t + slot) * 128, acc);
+    }
+  }
+  part_keys[2 * t] = pk0;
+  part_keys[2 * t + 1] = pk1;
+}
+
+// One thread per partial slot; the leftmost piece of each straddling run (not OPEN_LEFT) walks right
+// over slot 0 of the following chunks while the run stays open, and writes the bucket.
+template <class CF>
+__global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ part_keys,
+                                                 const void* __restrict__ part_pts, uint32_t n_chunks,
+                                                 void* __restrict__ buckets) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 2 * n_chunks) return;
+  uint32_t pk = part_keys[q];
+  if (pk == 0 || (pk & PK_OPEN_LEFT)) return;
+  Xyzz<CF> acc = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)q * 128);
+  uint32_t chunk = q >> 1;
+  while (pk & PK_OPEN_RIGHT) {
+    chunk++;
+    uint32_t nq = 2 * chunk;
+    pk = part_keys[nq];
+    Xyzz<CF> nxt = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)nq * 128);
+    xyzz_add(acc, nxt);
+  }
+  xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)(pk & PK_KEY_MASK) * 128, acc);
+}
+
+// ------------------------------------------------------------------ bucket reduction
+// buckets[1..B]; thread t owns b in [t*m+1, (t+1)*m]:  out[t] = sum (b - t*m) * bucket[b] + (t*m) * sum bucket[b]
+template <class CF>
+__global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets, uint32_t B, uint32_t m,
+                                                       void* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo = t * m;
+  if (lo >= B) return;
+  uint32_t hi = lo + m < B ? lo + m : B;
+  Xyzz<CF> run = xyzz_identity<CF>(), acc = xyzz_identity<CF>();
+  for (uint32_t b = hi; b > lo; b--) {
+    Xyzz<CF> bk = xyzz_load<CF>(reinterpret_cast<const char*>(buckets) + (size_t)b * 128);
+    xyzz_add(run, bk);
+    xyzz_add(acc, run);
+  }
+  if (lo) {
+    Xyzz<CF> w = xyzz_mul_u32(run, lo);
+    xyzz_add(acc, w);
+  }
+  xyzz_store<CF>(reinterpret_cast<char*>(out) + (size_t)t * 128, acc);
+}
+
+// Sum `n` XYZZ points into ceil(n / per_block) points: each block sums a contiguous slice.
+template <class CF>
+__global__ void __launch_bounds__(128) k_sum_points(const void* __restrict__ in, uint32_t n, uint32_t per_thread,
+                                                    void* __restrict__ out) {
+  __shared__ uint4 sm[128 * 8];   // 128 XYZZ points
+  uint32_t per_block = per_thread * blockDim.x;
+  uint32_t base = blockIdx.x * per_block + threadIdx.x * per_thread;
+  Xyzz<CF> acc = xyzz_identity<CF>();
+  for (uint32_t k = 0; k < per_thread; k++) {
+    uint32_t idx = base + k;
+    if (idx < n) {
+      Xyzz<CF> p = xyzz_load<CF>(reinterpret_cast<const char*>(in) + (size_t)idx * 128);
+      xyzz_add(acc, p);
+    }
+  }
+  char* my = reinterpret_cast<char*>(sm) + threadIdx.x * 128;
+  xyzz_store<CF>(my, acc);
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      Xyzz<CF> o = xyzz_load_shared<CF>(reinterpret_cast<char*>(sm) + (threadIdx.x + s) * 128);
+      xyzz_add(acc, o);
+      xyzz_store<CF>(my, acc);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) xyzz_store<CF>(reinterpret_cast<char*>(out) + (size_t)blockIdx.x * 128, acc);
+}
+
+template <class CF>
+__global__ void k_finalize(const void* __restrict__ in_xyzz, void* __restrict__ out_affine) {
+  if (threadIdx.x || blockIdx.x) return;
+  Xyzz<CF> p = xyzz_load<CF>(in_xyzz);
+  aff_store<CF>(out_affine, xyzz_to_affine(p));
+}
+
+// ------------------------------------------------------------------ fixed-base table
+// table[j*n + i] = 2^(c*j) * P_i in affine form, j = 0..W-1.  One thread per point walks the windows.
+template <class CF>
+__global__ void __launch_bounds__(128) k_precompute(const void* __restrict__ bases, uint32_t n, int c, int W,
+                                                    void* __restrict__ table) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<CF> p = aff_load<CF>(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
+  aff_store<CF>(reinterpret_cast<char*>(table) + (size_t)i * 64, p);
+  for (int j = 1; j < W; j++) {
+    Xyzz<CF> q = xyzz_from_affine(p);
+    for (int k = 0; k < c; k++) q = xyzz_dbl(q);
+    p = xyzz_to_affine(q);
+    aff_store<CF>(reinterpret_cast<char*>(table) + ((size_t)j * n + i) * 64, p);
+  }
+}
+
+// is_on_curve over the whole key (src/commitment.rs:145-146): flag != 0 if any point is off-curve
+template <class CF>
+__global__ void __launch_bounds__(256) k_check_on_curve(const void* __restrict__ bases, uint32_t n, uint32_t b_small,
+                                                        int b_negative, uint32_t* __restrict__ flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<CF> p = aff_load<CF>(reinterpret_cast<const char*>(bases) + (size_t)i * 64);
+  if (aff_is_identity(p)) return;
+  Fe<CF> bc = fe_zero<CF>();
+  bc.v[0] = b_small;
+  bc = fe_from_canonical(bc);
+  if (b_negative) bc = fe_neg(bc);
+  Fe<CF> lhs = fe_sqr(p.y);
+  Fe<CF> rhs = fe_add(fe_mul(fe_sqr(p.x), p.x), bc);
+  if (!fe_eq(lhs, rhs)) atomicOr(flag, 1u);
+}
+
+}  // namespace mira
