@@ -1,0 +1,92 @@
+// ctx.hpp — host-side context shared by the per-curve translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mira_b200.h"
+
+namespace mira_host {
+
+int fail(int code, const char* fmt, ...);   // records the thread-local error text, returns `code`
+
+#define CU(x)                                                                                          \
+  do {                                                                                                 \
+    cudaError_t e_ = (x);                                                                              \
+    if (e_ != cudaSuccess)                                                                             \
+      return ::mira_host::fail(MIRA_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return MIRA_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cap = bytes;
+    return MIRA_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// Fixed-base table for one window width: table[j * n_cover + i] = 2^(c*j) * P_i (affine, 64 B)
+struct Table {
+  int c = 0, W = 0;
+  uint32_t n_cover = 0;
+  void* d = nullptr;
+};
+
+inline int windows_for(int c) { return (255 + c - 1) / c; }
+int choose_window(size_t n);
+
+}  // namespace mira_host
+
+struct mira_msm_ctx {
+  int curve = 0;
+  int device = 0;
+  size_t n_bases = 0;
+  void* d_bases = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<mira_host::Table> tables;
+  // workspace (grown on demand, reused across commits)
+  mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
+  void* h_result = nullptr;  // pinned, 256 B
+  int forced_window = 0;
+  bool profiling = false;
+  mira_msm_stats stats{};
+  std::mutex mu;
+};
+
+namespace mira_host {
+
+// Per-curve entry points (curve_bn254.cu / curve_grumpkin.cu instantiate the templates in pipeline.cuh)
+struct CurveOps {
+  int (*commit)(mira_msm_ctx*, const void* scalars, size_t n, int on_device, void* out, bool want_affine, cudaStream_t st);
+  int (*prepare)(mira_msm_ctx*, size_t n);
+  int (*check_on_curve)(mira_msm_ctx*);
+  int (*combine)(const void* partials_host, size_t count, void* out_affine_host);
+  int (*gen_scalars)(uint64_t seed, size_t first, size_t n, int dist, void* out_dev);
+  int (*gen_bases)(uint64_t seed, size_t first, size_t n, void* out_dev);
+  int (*test_point_op)(int op, const void* p_dev, const void* q_dev, size_t n, void* out_dev);
+};
+extern const CurveOps OPS_BN254, OPS_GRUMPKIN;
+inline const CurveOps& ops_for(int curve) { return curve == MIRA_BN254_G1 ? OPS_BN254 : OPS_GRUMPKIN; }
+
+// field test hook (field_test.cu)
+int test_field_op_dev(int field, int op, const void* a_dev, const void* b_dev, size_t n, void* out_dev);
+
+}  // namespace mira_host

@@ -86,7 +86,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   return warp_off + x - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
                                                                  uint32_t* __restrict__ tile_sums) {
   __shared__ uint32_t sm[32];
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t*
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 // single block: in-place exclusive scan of up to SCAN_TILE*... tile sums (looped)
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(uint32_t* __restrict__ data, uint32_t n) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(uint32_t* __restrict__ data, uint32_t n) {
   __shared__ uint32_t sm[32];
   uint32_t running = 0;
   for (uint32_t base = 0; base < n; base += SCAN_THREADS) {
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(uint32_t* __restric
     running += total;
   }
 }
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
                                                              const uint32_t* __restrict__ tile_offsets,
                                                              uint32_t* __restrict__ out) {
   __shared__ uint32_t sm[32];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------ scatter (counting sort, v1)
-__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ refs,
+static __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ refs,
                                                  size_t n_entries, uint32_t* __restrict__ cursor,
                                                  uint32_t* __restrict__ skeys, uint32_t* __restrict__ srefs) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

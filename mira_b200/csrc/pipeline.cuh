@@ -1,0 +1,287 @@
+// pipeline.cuh — host orchestration of the MSM pipeline, templated on <coordinate field, scalar field>.
+// Instantiated once per curve (curve_bn254.cu, curve_grumpkin.cu) so the two curves compile in parallel.
+#pragma once
+#include "ctx.hpp"
+#include "msm_kernels.cuh"
+#include "testgen.cuh"
+
+namespace mira_host {
+using namespace mira;
+
+template <class CF>
+int build_table(mira_msm_ctx* ctx, int c, uint32_t n_cover, Table* out) {
+  int W = windows_for(c);
+  void* d = nullptr;
+  size_t bytes = (size_t)W * n_cover * 64;
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess)
+    return fail(MIRA_ERR_CUDA, "cudaMalloc(%zu) for the fixed-base table failed: %s", bytes, cudaGetErrorString(e));
+  k_precompute<CF><<<(n_cover + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_bases, n_cover, c, W, d);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(MIRA_ERR_CUDA, "k_precompute launch failed: %s", cudaGetErrorString(e));
+  }
+  out->c = c;
+  out->W = W;
+  out->n_cover = n_cover;
+  out->d = d;
+  return MIRA_OK;
+}
+
+// returns the table for window c covering at least n points (building it on first use)
+template <class CF>
+int get_table(mira_msm_ctx* ctx, int c, size_t n, Table** out) {
+  for (auto& t : ctx->tables)
+    if (t.c == c && t.n_cover >= n) {
+      *out = &t;
+      return MIRA_OK;
+    }
+  // cover a power-of-two prefix (commit lengths recur; the prefix keeps small commits on small tables)
+  size_t cover = 1;
+  while (cover < n) cover <<= 1;
+  if (cover > ctx->n_bases) cover = ctx->n_bases;
+  // drop a smaller table for the same c
+  for (auto it = ctx->tables.begin(); it != ctx->tables.end();) {
+    if (it->c == c) {
+      cudaFree(it->d);
+      it = ctx->tables.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  Table t;
+  int rc = build_table<CF>(ctx, c, (uint32_t)cover, &t);
+  if (rc) return rc;
+  ctx->tables.push_back(t);
+  *out = &ctx->tables.back();
+  return MIRA_OK;
+}
+
+struct PhaseTimer {
+  cudaEvent_t ev[6];
+  bool on;
+  cudaStream_t s;
+  PhaseTimer(bool enabled, cudaStream_t st) : on(enabled), s(st) {
+    if (on)
+      for (auto& e : ev) cudaEventCreate(&e);
+  }
+  void mark(int i) {
+    if (on) cudaEventRecord(ev[i], s);
+  }
+  float ms(int a, int b) {
+    float v = 0;
+    if (on) cudaEventElapsedTime(&v, ev[a], ev[b]);
+    return v;
+  }
+  ~PhaseTimer() {
+    if (on)
+      for (auto& e : ev) cudaEventDestroy(e);
+  }
+};
+
+// Runs the device pipeline; leaves the XYZZ sum (128 B) in ctx->result.p
+template <class CF, class SF>
+int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t st) {
+  uint64_t launches = 0;
+  int rc;
+  if ((rc = ctx->result.ensure(256))) return rc;
+  if (n == 0) {
+    CU(cudaMemsetAsync(ctx->result.p, 0, 128, st));
+    ctx->stats = mira_msm_stats{};
+    return MIRA_OK;
+  }
+  int c = ctx->forced_window ? ctx->forced_window : choose_window(n);
+  Table* tab = nullptr;
+  if ((rc = get_table<CF>(ctx, c, n, &tab))) return rc;
+  const int W = tab->W;
+  const size_t E = n * (size_t)W;
+  if (E >= (size_t)0x7fffffff || (size_t)W * tab->n_cover >= (size_t)0x7fffffff)
+    return fail(MIRA_ERR_INVALID, "commit of %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it", n, E);
+  const uint32_t B = 1u << (c - 1);
+
+  if ((rc = ctx->keys.ensure(E * 4)) || (rc = ctx->refs.ensure(E * 4)) || (rc = ctx->skeys.ensure(E * 4 + 16)) ||
+      (rc = ctx->srefs.ensure(E * 4)) || (rc = ctx->counts.ensure(((size_t)B + 2) * 4)) ||
+      (rc = ctx->cursor.ensure(((size_t)B + 2) * 4)) || (rc = ctx->buckets.ensure(((size_t)B + 1) * 128)))
+    return rc;
+  const uint32_t n_counts = B + 1;
+  const uint32_t n_tiles = (n_counts + SCAN_TILE - 1) / SCAN_TILE;
+  if ((rc = ctx->tile_sums.ensure((size_t)n_tiles * 4 + 16))) return rc;
+
+  PhaseTimer pt(ctx->profiling, st);
+  pt.mark(0);
+  // ---- digits + histogram
+  CU(cudaMemsetAsync(ctx->counts.p, 0, ((size_t)B + 2) * 4, st));
+  k_digits<SF><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, tab->n_cover, (uint32_t*)ctx->keys.p,
+                                                           (uint32_t*)ctx->refs.p, (uint32_t*)ctx->counts.p);
+  launches++;
+  pt.mark(1);
+  // ---- exclusive scan of the histogram -> bucket start offsets, then scatter
+  k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->counts.p, n_counts, (uint32_t*)ctx->tile_sums.p);
+  k_scan_small<<<1, SCAN_THREADS, 0, st>>>((uint32_t*)ctx->tile_sums.p, n_tiles + 1);
+  k_scan_apply<<<n_tiles, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->counts.p, n_counts, (const uint32_t*)ctx->tile_sums.p,
+                                                 (uint32_t*)ctx->cursor.p);
+  k_scatter<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((const uint32_t*)ctx->keys.p, (const uint32_t*)ctx->refs.p, E,
+                                                        (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p);
+  launches += 4;
+  // number of non-zero entries = tile_sums[n_tiles] after the scan (total); read it back
+  uint32_t n_sorted = 0;
+  CU(cudaMemcpyAsync(&n_sorted, (uint32_t*)ctx->tile_sums.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  pt.mark(2);
+  // ---- accumulate
+  CU(cudaMemsetAsync(ctx->buckets.p, 0, ((size_t)B + 1) * 128, st));
+  if (n_sorted) {
+    const int L = 32;
+    uint32_t n_chunks = (n_sorted + L - 1) / L;
+    if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
+    k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->skeys.p, (const uint32_t*)ctx->srefs.p, n_sorted, L,
+                                                            tab->d, ctx->buckets.p, (uint32_t*)ctx->part_keys.p, ctx->part_pts.p);
+    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, n_chunks, ctx->buckets.p);
+    launches += 2;
+  }
+  pt.mark(3);
+  // ---- bucket reduction
+  const uint32_t m = B >= (1u << 14) ? 32 : (B >= 1024 ? 8 : 1);
+  uint32_t n_red = (B + m - 1) / m;
+  if ((rc = ctx->red_a.ensure((size_t)n_red * 128)) || (rc = ctx->red_b.ensure((size_t)(n_red / 128 + 2) * 128))) return rc;
+  k_reduce_chunks<CF><<<(n_red + 127) / 128, 128, 0, st>>>(ctx->buckets.p, B, m, ctx->red_a.p);
+  launches++;
+  void* src = ctx->red_a.p;
+  void* dst = ctx->red_b.p;
+  uint32_t cnt = n_red;
+  while (cnt > 1) {
+    uint32_t per_thread = cnt > 128 * 8 ? 8 : 1;
+    uint32_t per_block = per_thread * 128;
+    uint32_t blocks = (cnt + per_block - 1) / per_block;
+    k_sum_points<CF><<<blocks, 128, 0, st>>>(src, cnt, per_thread, dst);
+    launches++;
+    cnt = blocks;
+    std::swap(src, dst);
+  }
+  CU(cudaMemcpyAsync(ctx->result.p, src, 128, cudaMemcpyDeviceToDevice, st));
+  pt.mark(4);
+  CU(cudaGetLastError());
+  ctx->stats.window_bits = c;
+  ctx->stats.windows = W;
+  ctx->stats.entries = E;
+  ctx->stats.buckets = B;
+  ctx->stats.kernel_launches = launches;
+  if (ctx->profiling) {
+    CU(cudaStreamSynchronize(st));
+    ctx->stats.ms_digits = pt.ms(0, 1);
+    ctx->stats.ms_sort = pt.ms(1, 2);
+    ctx->stats.ms_accumulate = pt.ms(2, 3);
+    ctx->stats.ms_reduce = pt.ms(3, 4);
+    ctx->stats.ms_total = pt.ms(0, 4);
+  }
+  return MIRA_OK;
+}
+
+template <class CF, class SF>
+int commit_impl(mira_msm_ctx* ctx, const void* scalars, size_t n, int on_device, void* out, bool want_affine, cudaStream_t st) {
+  int rc;
+  const void* d_scalars = scalars;
+  if (!on_device && n) {
+    if ((rc = ctx->scalars.ensure(n * 32))) return rc;
+    CU(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    d_scalars = ctx->scalars.p;
+  }
+  if ((rc = msm_device<CF, SF>(ctx, d_scalars, n, st))) return rc;
+  if (want_affine) {
+    k_finalize<CF><<<1, 32, 0, st>>>(ctx->result.p, (char*)ctx->result.p + 128);
+    ctx->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_result, (char*)ctx->result.p + 128, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(out, ctx->h_result, 64);
+  } else {
+    CU(cudaMemcpyAsync(ctx->h_result, ctx->result.p, 128, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(out, ctx->h_result, 128);
+  }
+  return MIRA_OK;
+}
+
+
+template <class CF>
+int prepare_impl(mira_msm_ctx* ctx, size_t n) {
+  int c = ctx->forced_window ? ctx->forced_window : choose_window(n);
+  Table* t = nullptr;
+  int rc = get_table<CF>(ctx, c, n, &t);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MIRA_OK;
+}
+
+template <class CF>
+int check_on_curve_impl(mira_msm_ctx* ctx, uint32_t b_small, int b_negative) {
+  int rc;
+  if ((rc = ctx->result.ensure(256))) return rc;
+  uint32_t* flag = (uint32_t*)((char*)ctx->result.p + 192);
+  CU(cudaMemsetAsync(flag, 0, 4, ctx->stream));
+  if (ctx->n_bases) {
+    unsigned blocks = (unsigned)((ctx->n_bases + 255) / 256);
+    k_check_on_curve<CF><<<blocks, 256, 0, ctx->stream>>>(ctx->d_bases, (uint32_t)ctx->n_bases, b_small, b_negative, flag);
+  }
+  uint32_t h = 0;
+  CU(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (h) return fail(MIRA_ERR_NOT_ON_CURVE, "Wrong file in cache, some ptr out of curve");
+  return MIRA_OK;
+}
+
+template <class CF>
+int combine_impl(const void* partials, size_t count, void* out_affine) {
+  void* d = nullptr;
+  size_t bytes = (count + 2) * 128;
+  CU(cudaMalloc(&d, bytes * 2));
+  cudaError_t e = cudaMemset(d, 0, bytes * 2);
+  if (e == cudaSuccess && count) e = cudaMemcpy(d, partials, count * 128, cudaMemcpyHostToDevice);
+  void* src = d;
+  void* dst = (char*)d + bytes;
+  uint32_t cnt = count ? (uint32_t)count : 1;
+  while (e == cudaSuccess && cnt > 1) {
+    uint32_t blocks = (cnt + 127) / 128;
+    k_sum_points<CF><<<blocks, 128>>>(src, cnt, 1, dst);
+    cnt = blocks;
+    std::swap(src, dst);
+  }
+  if (e == cudaSuccess) {
+    k_finalize<CF><<<1, 32>>>(src, (char*)dst);
+    e = cudaMemcpy(out_affine, dst, 64, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "combine failed: %s", cudaGetErrorString(e));
+  return MIRA_OK;
+}
+
+template <class SF>
+int gen_scalars_impl(uint64_t seed, size_t first, size_t n, int dist, void* out_dev) {
+  k_gen_scalars<SF><<<(unsigned)((n + 255) / 256), 256>>>(seed, first, n, dist, out_dev);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return MIRA_OK;
+}
+
+template <class CF, class SF>
+int gen_bases_impl(uint64_t seed, size_t first, size_t n, void* out_dev) {
+  void* table = nullptr;
+  CU(cudaMalloc(&table, 32 * 256 * 64));
+  k_gen_table<CF><<<32 * 256 / 128, 128>>>(table);
+  k_gen_bases<CF, SF><<<(unsigned)((n + 127) / 128), 128>>>(seed, first, n, table, out_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(table);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "gen_bases failed: %s", cudaGetErrorString(e));
+  return MIRA_OK;
+}
+
+template <class CF>
+int test_point_op_impl(int op, const void* p, const void* q, size_t n, void* out) {
+  k_test_point<CF><<<(unsigned)((n + 127) / 128), 128>>>(op, p, q, n, out);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return MIRA_OK;
+}
+
+}  // namespace mira_host
