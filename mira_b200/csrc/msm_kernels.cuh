@@ -3,7 +3,7 @@
 // Replaces halo2_proofs::arithmetic::best_multiexp as called from CommitmentKey::commit
 // (/root/reference/src/commitment.rs:78-87).  Pipeline:
 //   k_digits      scalar: Montgomery -> canonical, signed c-bit digits, (bucket, point-ref) pairs
-//   sort          group the n*W pairs by bucket
+//   sort          group the pairs by bucket (sort.cu: LSD radix sort staged through shared memory)
 //   k_accumulate  load-balanced segmented XYZZ mixed-add over the sorted list (fixed-size chunks)
 //   k_combine     stitch runs that straddle chunk boundaries
 //   k_reduce_*    S = sum_b b * bucket[b] by chunked running sums + tree sum
@@ -21,127 +21,79 @@ constexpr uint32_t PK_OPEN_RIGHT = 0x40000000u; // partial's run continues in th
 constexpr uint32_t PK_KEY_MASK = 0x3fffffffu;
 
 // ------------------------------------------------------------------ digits
-// One thread per scalar.  keys/refs are window-major (entry j*n + i) so warps write coalesced rows.
-// digit d_j in [-2^(c-1)+1, 2^(c-1)]; key = |d_j| (0 = nothing to add), ref = j*n_cover + i | sign.
-template <class SF>
-__global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars, uint32_t n, int c, int W,
-                                                uint32_t n_cover, uint32_t* __restrict__ keys,
-                                                uint32_t* __restrict__ refs, uint32_t* __restrict__ counts) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fe<SF> s = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + (size_t)i * 32));
+// One thread per scalar: Montgomery -> canonical, then W signed c-bit digits d_j in [-2^(c-1)+1, 2^(c-1)].
+// Every non-zero digit becomes one (key, ref) pair: key = |d_j| (the bucket), ref = j*n_cover + i with the
+// sign in bit 31 (j*n_cover + i indexes the fixed-base table entry 2^(c*j) * P_i).  Zero digits are dropped
+// here (witness-like scalars are mostly zero), so the pair list is compacted: a block counts its pairs,
+// reserves a range with ONE atomicAdd, and each warp writes window by window at ballot-derived positions,
+// i.e. 128-byte coalesced rows.  *n_out receives the total number of pairs.
+constexpr int DG_THREADS = 256;
+constexpr int DG_WARPS = DG_THREADS / 32;
+
+__device__ __forceinline__ uint32_t signed_digit(const uint32_t (&s)[8], int j, int c, uint32_t& carry, uint32_t& neg) {
   const uint32_t half = 1u << (c - 1);
-  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
-  uint32_t carry = 0;
+  const uint32_t mask = (1u << c) - 1u;     // c <= 26
+  int bit = j * c;
+  int w = bit >> 5, sh = bit & 31;
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {             // register-resident select instead of dynamic indexing
+    if (k == w) lo = s[k];
+    if (k == w + 1) hi = s[k];
+  }
+  uint32_t d = (sh ? ((lo >> sh) | (hi << (32 - sh))) : lo) & mask;
+  d += carry;
+  neg = 0;
+  carry = 0;
+  if (d > half) {                            // d in (half, 2^c] -> d - 2^c in (-half, 0]
+    d = (1u << c) - d;
+    neg = d ? REF_NEG : 0u;
+    carry = 1;
+  }
+  return d;
+}
+
+template <class SF>
+__global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ scalars, uint32_t n, int c, int W,
+                                                       uint32_t n_cover, uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ refs, uint32_t* __restrict__ n_out) {
+  extern __shared__ uint32_t sm_cnt[];       // [W][DG_WARPS] pair counts -> offsets, then [0] = block base
+  __shared__ uint32_t sm_base;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool valid = i < n;
+  Fe<SF> s = fe_zero<SF>();
+  if (valid) s = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + (size_t)i * 32));
+  // pass 1: count the non-zero digits per (window, warp)
+  uint32_t carry = 0, neg;
   for (int j = 0; j < W; j++) {
-    int bit = j * c;
-    int w = bit >> 5, sh = bit & 31;
-    uint32_t lo = (w < 8) ? s.v[w] : 0u;
-    uint32_t hi = (w + 1 < 8) ? s.v[w + 1] : 0u;
-    uint32_t d = (sh ? ((lo >> sh) | (hi << (32 - sh))) : lo) & mask;
-    d += carry;
-    uint32_t neg = 0;
-    carry = 0;
-    if (d > half) {           // d in (half, 2^c] -> d - 2^c in (-half, 0]
-      d = (1u << c) - d;
-      neg = (d != 0) ? REF_NEG : 0u;
-      carry = 1;
+    uint32_t d = signed_digit(s.v, j, c, carry, neg);
+    uint32_t b = __ballot_sync(0xffffffffu, d != 0);
+    if (lane == 0) sm_cnt[j * DG_WARPS + warp] = __popc(b);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                    // W*8 <= 1024 values: a serial scan is cheap next to W digit loops
+    uint32_t run = 0;
+    for (int k = 0; k < W * DG_WARPS; k++) {
+      uint32_t t = sm_cnt[k];
+      sm_cnt[k] = run;
+      run += t;
     }
-    size_t e = (size_t)j * n + i;
-    keys[e] = d;
-    refs[e] = ((uint32_t)j * n_cover + i) | neg;
-    if (d) atomicAdd(&counts[d], 1u);
+    sm_base = run ? atomicAdd(n_out, run) : 0u;
   }
-}
-
-// ------------------------------------------------------------------ exclusive scan (3 phases)
-constexpr int SCAN_THREADS = 512;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem, uint32_t& total) {
-  // smem: blockDim.x / 32 words
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t x = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) smem[warp] = x;
   __syncthreads();
-  if (warp == 0) {
-    uint32_t w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0u;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += y;
+  const uint32_t base = sm_base;
+  const uint32_t lt = (1u << lane) - 1u;
+  carry = 0;
+  for (int j = 0; j < W; j++) {
+    uint32_t d = signed_digit(s.v, j, c, carry, neg);
+    uint32_t b = __ballot_sync(0xffffffffu, d != 0);
+    if (d) {
+      uint32_t pos = base + sm_cnt[j * DG_WARPS + warp] + __popc(b & lt);
+      keys[pos] = d;
+      refs[pos] = ((uint32_t)j * n_cover + i) | neg;
     }
-    smem[lane] = w;   // inclusive warp totals (blockDim/32 <= 32)
   }
-  __syncthreads();
-  uint32_t warp_off = warp ? smem[warp - 1] : 0u;
-  total = smem[(blockDim.x >> 5) - 1];
-  __syncthreads();
-  return warp_off + x - v;
-}
-
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
-                                                                 uint32_t* __restrict__ tile_sums) {
-  __shared__ uint32_t sm[32];
-  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? in[base + k] : 0u;
-  uint32_t total;
-  block_exclusive_scan(s, sm, total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-// single block: in-place exclusive scan of up to SCAN_TILE*... tile sums (looped)
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(uint32_t* __restrict__ data, uint32_t n) {
-  __shared__ uint32_t sm[32];
-  uint32_t running = 0;
-  for (uint32_t base = 0; base < n; base += SCAN_THREADS) {
-    uint32_t idx = base + threadIdx.x;
-    uint32_t v = (idx < n) ? data[idx] : 0u;
-    uint32_t total;
-    uint32_t ex = block_exclusive_scan(v, sm, total);
-    if (idx < n) data[idx] = running + ex;
-    running += total;
-  }
-}
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
-                                                             const uint32_t* __restrict__ tile_offsets,
-                                                             uint32_t* __restrict__ out) {
-  __shared__ uint32_t sm[32];
-  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  uint32_t v[SCAN_ITEMS];
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = (base + k < n) ? in[base + k] : 0u;
-    s += v[k];
-  }
-  uint32_t total;
-  uint32_t ex = block_exclusive_scan(s, sm, total) + tile_offsets[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < n) out[base + k] = ex;
-    ex += v[k];
-  }
-}
-
-// ------------------------------------------------------------------ scatter (counting sort, v1)
-static __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ refs,
-                                                 size_t n_entries, uint32_t* __restrict__ cursor,
-                                                 uint32_t* __restrict__ skeys, uint32_t* __restrict__ srefs) {
-  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_entries) return;
-  uint32_t k = keys[e];
-  if (k == 0) return;
-  uint32_t pos = atomicAdd(&cursor[k], 1u);
-  skeys[pos] = k;
-  srefs[pos] = refs[e];
 }
 
 // ------------------------------------------------------------------ accumulate
@@ -161,9 +113,11 @@ __device__ __forceinline__ Affine<CF> load_ref(const void* __restrict__ table, u
 
 template <class CF>
 __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ skeys,
-                                                    const uint32_t* __restrict__ srefs, uint32_t n_sorted, int L,
+                                                    const uint32_t* __restrict__ srefs,
+                                                    const uint32_t* __restrict__ n_ptr, int L,
                                                     const void* __restrict__ table, void* __restrict__ buckets,
                                                     uint32_t* __restrict__ part_keys, void* __restrict__ part_pts) {
+  const uint32_t n_sorted = *n_ptr;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   size_t begin = (size_t)t * L;
   if (begin >= n_sorted) return;
@@ -211,8 +165,10 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
 // over slot 0 of the following chunks while the run stays open, and writes the bucket.
 template <class CF>
 __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ part_keys,
-                                                 const void* __restrict__ part_pts, uint32_t n_chunks,
+                                                 const void* __restrict__ part_pts,
+                                                 const uint32_t* __restrict__ n_ptr, int L,
                                                  void* __restrict__ buckets) {
+  const uint32_t n_chunks = (*n_ptr + L - 1) / L;
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= 2 * n_chunks) return;
   uint32_t pk = part_keys[q];

@@ -100,44 +100,41 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
     return fail(MIRA_ERR_INVALID, "commit of %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it", n, E);
   const uint32_t B = 1u << (c - 1);
 
-  if ((rc = ctx->keys.ensure(E * 4)) || (rc = ctx->refs.ensure(E * 4)) || (rc = ctx->skeys.ensure(E * 4 + 16)) ||
-      (rc = ctx->srefs.ensure(E * 4)) || (rc = ctx->counts.ensure(((size_t)B + 2) * 4)) ||
-      (rc = ctx->cursor.ensure(((size_t)B + 2) * 4)) || (rc = ctx->buckets.ensure(((size_t)B + 1) * 128)))
+  if ((rc = ctx->keys.ensure(E * 4 + 16)) || (rc = ctx->refs.ensure(E * 4 + 16)) || (rc = ctx->skeys.ensure(E * 4 + 16)) ||
+      (rc = ctx->srefs.ensure(E * 4 + 16)) || (rc = ctx->counts.ensure(64)) || (rc = ctx->buckets.ensure(((size_t)B + 1) * 128)) ||
+      (rc = ctx->tile_sums.ensure(radix_sort_temp_bytes(E))))
     return rc;
-  const uint32_t n_counts = B + 1;
-  const uint32_t n_tiles = (n_counts + SCAN_TILE - 1) / SCAN_TILE;
-  if ((rc = ctx->tile_sums.ensure((size_t)n_tiles * 4 + 16))) return rc;
+  uint32_t* d_npairs = (uint32_t*)ctx->counts.p;     // number of (bucket, ref) pairs, produced on the device
 
   PhaseTimer pt(ctx->profiling, st);
   pt.mark(0);
-  // ---- digits + histogram
-  CU(cudaMemsetAsync(ctx->counts.p, 0, ((size_t)B + 2) * 4, st));
-  k_digits<SF><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, tab->n_cover, (uint32_t*)ctx->keys.p,
-                                                           (uint32_t*)ctx->refs.p, (uint32_t*)ctx->counts.p);
+  // ---- digits (compacted pair list)
+  CU(cudaMemsetAsync(d_npairs, 0, 4, st));
+  k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
+      d_scalars, (uint32_t)n, c, W, tab->n_cover, (uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, d_npairs);
   launches++;
   pt.mark(1);
-  // ---- exclusive scan of the histogram -> bucket start offsets, then scatter
-  k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->counts.p, n_counts, (uint32_t*)ctx->tile_sums.p);
-  k_scan_small<<<1, SCAN_THREADS, 0, st>>>((uint32_t*)ctx->tile_sums.p, n_tiles + 1);
-  k_scan_apply<<<n_tiles, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->counts.p, n_counts, (const uint32_t*)ctx->tile_sums.p,
-                                                 (uint32_t*)ctx->cursor.p);
-  k_scatter<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((const uint32_t*)ctx->keys.p, (const uint32_t*)ctx->refs.p, E,
-                                                        (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p);
-  launches += 4;
-  // number of non-zero entries = tile_sums[n_tiles] after the scan (total); read it back
-  uint32_t n_sorted = 0;
-  CU(cudaMemcpyAsync(&n_sorted, (uint32_t*)ctx->tile_sums.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  // ---- group pairs by bucket: LSD radix sort on the c-bit key
+  int in_b = 0;
+  if ((rc = radix_sort_pairs((uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p, d_npairs, E, c,
+                             ctx->tile_sums.p, st, &in_b, &launches)))
+    return rc;
+  const uint32_t* skeys = (const uint32_t*)(in_b ? ctx->skeys.p : ctx->keys.p);
+  const uint32_t* srefs = (const uint32_t*)(in_b ? ctx->srefs.p : ctx->refs.p);
   pt.mark(2);
   // ---- accumulate
   CU(cudaMemsetAsync(ctx->buckets.p, 0, ((size_t)B + 1) * 128, st));
-  if (n_sorted) {
-    const int L = 32;
-    uint32_t n_chunks = (n_sorted + L - 1) / L;
+  {
+    // Entries per thread: as long as possible (each chunk edge that falls inside a bucket's run costs one
+    // XYZZ full add in k_combine) while keeping >= ~4 waves of 148 SMs x 512 resident threads.  Sized from
+    // the upper bound n*W; grids cover that bound and surplus threads exit on the device-side pair count.
+    int L = (int)(E / (148u * 512u * 4u));
+    L = L < 16 ? 16 : (L > 256 ? 256 : L);
+    uint32_t n_chunks = (uint32_t)((E + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
-    k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->skeys.p, (const uint32_t*)ctx->srefs.p, n_sorted, L,
-                                                            tab->d, ctx->buckets.p, (uint32_t*)ctx->part_keys.p, ctx->part_pts.p);
-    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, n_chunks, ctx->buckets.p);
+    k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(skeys, srefs, d_npairs, L, tab->d, ctx->buckets.p,
+                                                            (uint32_t*)ctx->part_keys.p, ctx->part_pts.p);
+    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L, ctx->buckets.p);
     launches += 2;
   }
   pt.mark(3);
