@@ -162,19 +162,37 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
 }
 
 // One thread per partial slot; the leftmost piece of each straddling run (not OPEN_LEFT) walks right
-// over slot 0 of the following chunks while the run stays open, and writes the bucket.
+// over slot 0 of the following chunks while the run stays open, and writes the bucket.  A run that
+// spans more than HEAVY_CHUNKS chunks (a "heavy" bucket: witness-like scalars put a large share of all
+// pairs into a few buckets) is not walked serially: its leader chunk is appended to `heavy` and
+// k_combine_heavy folds its pieces with a whole block.
+constexpr uint32_t HEAVY_CHUNKS = 8;
+
 template <class CF>
-__global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ part_keys,
+__global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ skeys,
+                                                 const uint32_t* __restrict__ part_keys,
                                                  const void* __restrict__ part_pts,
                                                  const uint32_t* __restrict__ n_ptr, int L,
-                                                 void* __restrict__ buckets) {
-  const uint32_t n_chunks = (*n_ptr + L - 1) / L;
+                                                 void* __restrict__ buckets, uint32_t* __restrict__ heavy,
+                                                 uint32_t heavy_cap) {
+  const uint32_t n = *n_ptr;
+  const uint32_t n_chunks = (n + L - 1) / L;
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= 2 * n_chunks) return;
   uint32_t pk = part_keys[q];
   if (pk == 0 || (pk & PK_OPEN_LEFT)) return;
-  Xyzz<CF> acc = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)q * 128);
   uint32_t chunk = q >> 1;
+  {
+    uint64_t probe = (uint64_t)(chunk + HEAVY_CHUNKS) * (uint32_t)L;
+    if (probe < n && skeys[probe] == (pk & PK_KEY_MASK)) {
+      uint32_t slot = atomicAdd(&heavy[0], 1u);
+      if (slot < heavy_cap) {            // heavy_cap >= n_chunks / HEAVY_CHUNKS + 1: cannot overflow
+        heavy[1 + slot] = q;
+        return;
+      }
+    }
+  }
+  Xyzz<CF> acc = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)q * 128);
   while (pk & PK_OPEN_RIGHT) {
     chunk++;
     uint32_t nq = 2 * chunk;
@@ -183,6 +201,54 @@ __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ pa
     xyzz_add(acc, nxt);
   }
   xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)(pk & PK_KEY_MASK) * 128, acc);
+}
+
+// One block per heavy run (grid-stride over the heavy list).  The run's pieces are the leader slot q0 and
+// slot 0 of chunks t0+1 .. t1, where t1 is the last chunk whose first pair still carries the key (binary
+// search over the sorted keys).  Threads sum pieces strided, then a shared-memory tree folds the block.
+constexpr int HV_THREADS = 256;
+template <class CF>
+__global__ void __launch_bounds__(HV_THREADS) k_combine_heavy(const uint32_t* __restrict__ skeys,
+                                                              const uint32_t* __restrict__ part_keys,
+                                                              const void* __restrict__ part_pts,
+                                                              const uint32_t* __restrict__ n_ptr, int L,
+                                                              void* __restrict__ buckets,
+                                                              const uint32_t* __restrict__ heavy, uint32_t heavy_cap) {
+  __shared__ uint4 sm[HV_THREADS * 8];
+  const uint32_t n = *n_ptr;
+  const uint32_t n_chunks = (n + L - 1) / L;
+  uint32_t n_heavy = heavy[0] < heavy_cap ? heavy[0] : heavy_cap;
+  for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    const uint32_t q0 = heavy[1 + h];
+    const uint32_t key = part_keys[q0] & PK_KEY_MASK;
+    const uint32_t t0 = q0 >> 1;
+    // t1 = largest chunk index with skeys[t1 * L] == key  (keys are sorted, chunk t0+1 qualifies)
+    uint32_t lo = t0 + 1, hi = n_chunks - 1;
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo + 1) / 2;
+      if (skeys[(uint64_t)mid * (uint32_t)L] <= key) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t t1 = lo;
+    Xyzz<CF> acc = xyzz_identity<CF>();
+    if (threadIdx.x == 0) acc = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)q0 * 128);
+    for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += HV_THREADS) {
+      Xyzz<CF> p = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)(2 * t) * 128);
+      xyzz_add(acc, p);
+    }
+    char* my = reinterpret_cast<char*>(sm) + threadIdx.x * 128;
+    xyzz_store<CF>(my, acc);
+    __syncthreads();
+    for (int s = HV_THREADS >> 1; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        Xyzz<CF> o = xyzz_load_shared<CF>(reinterpret_cast<char*>(sm) + (threadIdx.x + s) * 128);
+        xyzz_add(acc, o);
+        xyzz_store<CF>(my, acc);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)key * 128, acc);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------ bucket reduction

@@ -134,8 +134,15 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
     k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(skeys, srefs, d_npairs, L, tab->d, ctx->buckets.p,
                                                             (uint32_t*)ctx->part_keys.p, ctx->part_pts.p);
-    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L, ctx->buckets.p);
-    launches += 2;
+    uint32_t heavy_cap = n_chunks / HEAVY_CHUNKS + 2;
+    if ((rc = ctx->cursor.ensure(((size_t)heavy_cap + 2) * 4))) return rc;
+    uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0] = count, [1..] = leader slots of heavy runs
+    CU(cudaMemsetAsync(d_heavy, 0, 4, st));
+    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
+                                                             ctx->buckets.p, d_heavy, heavy_cap);
+    k_combine_heavy<CF><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
+                                                       ctx->buckets.p, d_heavy, heavy_cap);
+    launches += 3;
   }
   pt.mark(3);
   // ---- bucket reduction
