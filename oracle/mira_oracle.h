@@ -74,6 +74,51 @@ void oracle_commit_naive(int curve, const void *bases, const void *scalars, size
 void oracle_gen_scalars(int curve, uint64_t seed, size_t first, size_t n, int dist, void *out);
 void oracle_gen_bases(int curve, uint64_t seed, size_t first, size_t n, int threads, void *out);
 
+/* ==== witness side (mira_oracle_witness.c): rows a5, a7-a9, a12 of SURVEY.md §8 ==================== */
+
+/* RelaxedPlonkWitness::fold (src/plonk/mod.rs:1097-1134): out[i] = w1[i] + r*w2[i] */
+void oracle_fold_w(int field, const void *w1, const void *w2, size_t n, const void *r, void *out);
+/* out[i] = e[i] + sum_k r^(k+1) * terms[k][i] */
+void oracle_fold_e(int field, const void *e, const void *const *terms, size_t n_terms, size_t n, const void *r,
+                   void *out);
+/* util::concatenate_with_padding (src/util.rs:189-193); returns elements written (out may be NULL) */
+size_t oracle_concat_pad(const void *const *cols, const size_t *lens, size_t n_cols, size_t pad_size, void *out);
+
+/* PlonkEvalDomain (src/plonk/eval.rs:93-106) as plain pointers; all HOST memory here. */
+typedef struct {
+  uint64_t row_size;                 /* GetDataForEval::row_size() */
+  uint32_t num_selectors, num_fixed, num_advice, num_lookup, num_challenges, num_w1, num_w2, _pad;
+  const void *const *selectors;      /* [num_selectors] -> row_size bytes (Vec<bool>: 0/1 per row) */
+  const void *const *fixed;          /* [num_fixed]     -> row_size x 32 B */
+  const void *const *w1;             /* W1s[i] */
+  const uint64_t *w1_len;            /* W1s[i].len() in elements */
+  const void *const *w2;             /* W2s[i] */
+  const uint64_t *w2_len;
+  const void *challenges;            /* num_challenges x 32 B */
+} oracle_eval_domain;
+
+/* plonk::eval::Error (src/plonk/eval.rs:3-25) */
+enum {
+  ORACLE_EVAL_OK = 0,
+  ORACLE_EVAL_CHALLENGE_OUT_OF_BOUNDARY = -11,
+  ORACLE_EVAL_COLUMN_OUT_OF_BOUNDARY = -12,
+  ORACLE_EVAL_ROW_OUT_OF_BOUNDARY = -13,
+  ORACLE_EVAL_INVALID_WITNESS_INDEX = -14,
+  ORACLE_EVAL_BAD_PROGRAM = -15
+};
+/* GraphEvaluator::evaluate for rows [row_begin, row_end) of a serialised program (encoding: see
+ * include/mira_b200.h, mira_eval_program_create).  out: (row_end-row_begin) x 32 B. */
+int oracle_eval_rows(int field, const uint32_t *code, size_t code_words, const void *constants, size_t n_constants,
+                     const int32_t *rotations, size_t n_rotations, uint32_t num_intermediates,
+                     const oracle_eval_domain *dom, size_t row_begin, size_t row_end, void *out);
+
+/* fft::best_fft (src/fft.rs:51-115) in place over 2^log_n elements, and its helpers / wrappers */
+void oracle_fft(int field, void *a, uint32_t log_n, const void *omega);
+int  oracle_fft_omega(int field, uint32_t k, int is_inverse, void *out);   /* get_omega_or_inv; -1 if k > S */
+void oracle_fft_divisor(int field, uint32_t k, void *out);                 /* get_ifft_divisor */
+int  oracle_fft_forward(int field, void *a, uint32_t log_n);               /* fft  (src/fft.rs:160-162) */
+int  oracle_fft_inverse(int field, void *a, uint32_t log_n);               /* ifft (src/fft.rs:165-175) */
+
 int oracle_num_cores(void);
 
 #ifdef __cplusplus

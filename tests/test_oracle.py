@@ -216,3 +216,21 @@ def test_commit_is_homomorphism(curve):
     assert cf == O.point_add(curve, ca, rcb)
     # prefix-of-key semantics: a shorter vector uses ck[..len]
     assert O.commit(curve, bases, enc(a[:100])) == O.commit(curve, bases[:64 * 100], enc(a[:100]))
+
+
+def test_golden_commit_vectors_freeze_the_oracle():
+    """tests/golden/commit_vectors.json (ORACLE-GENERATED, see tests/golden/make_golden.py): the oracle and its
+    input generators still produce the committed bytes."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "commit_vectors.json")) as f:
+        vecs = json.load(f)
+    for v in vecs:
+        bases = O.gen_bases(v["curve"], v["seed_bases"], v["n"])
+        sc = O.gen_scalars(v["curve"], v["seed_scalars"], v["n"], v["dist"])
+        assert hashlib.sha256(bases).hexdigest() == v["bases_sha256"]
+        assert hashlib.sha256(sc).hexdigest() == v["scalars_sha256"]
+        assert O.commit(v["curve"], bases, sc).hex() == v["commit_hex"]
+        if v["n"] <= 64:
+            assert O.commit_naive(v["curve"], bases, sc).hex() == v["commit_hex"]
