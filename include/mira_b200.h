@@ -32,7 +32,13 @@ enum {
   MIRA_ERR_TOO_LONG_INPUT = -1, /* commitment::Error::TooLongInput, src/commitment.rs:20-24,82-85 */
   MIRA_ERR_CUDA = -2,           /* any CUDA failure; the reference has no such path => caller aborts */
   MIRA_ERR_INVALID = -3,        /* bad argument (null pointer, unknown curve, ...) */
-  MIRA_ERR_NOT_ON_CURVE = -4    /* load_or_setup_cache's check, src/commitment.rs:145-153 */
+  MIRA_ERR_NOT_ON_CURVE = -4,   /* load_or_setup_cache's check, src/commitment.rs:145-153 */
+  /* plonk::eval::Error (src/plonk/eval.rs:3-25), raised when a program is bound to a domain */
+  MIRA_ERR_EVAL_CHALLENGE = -11,     /* ChallengeIndexOutOfBoundary */
+  MIRA_ERR_EVAL_COLUMN = -12,        /* ColumnVariableIndexOutOfBoundary */
+  MIRA_ERR_EVAL_ROW = -13,           /* RowIndexOutOfBoundary */
+  MIRA_ERR_EVAL_WITNESS_INDEX = -14, /* InvalidWitnessIndex */
+  MIRA_ERR_EVAL_PROGRAM = -15        /* malformed program encoding (no reference analogue) */
 };
 
 /* Text of the last error raised on the calling thread ("" if none). */
@@ -92,6 +98,87 @@ int mira_msm_set_profiling(mira_msm_ctx *ctx, int enabled);
 /* override the window width chosen by the size heuristic (0 = automatic). */
 int mira_msm_set_window(mira_msm_ctx *ctx, int window_bits);
 
+/* ==== field vectors in HBM: the witness side of the hot path =====
+ * `field` is the SCALAR field of the curve being committed to: MIRA_FR for BN254 G1, MIRA_FQ for
+ * Grumpkin G1.  Every *_dev pointer is device memory on `device`; elements are 32 B Montgomery form.
+ * `stream` is a cudaStream_t (NULL = the legacy default stream).  All calls are asynchronous on that
+ * stream unless noted, so their outputs can feed mira_msm_commit_device without touching the host. */
+
+/* RelaxedPlonkWitness::fold, W part (src/plonk/mod.rs:1100-1110): out[i] = w1[i] + r * w2[i].
+ * r_host: 32 B on the host.  out_dev may alias w1_dev. */
+int mira_fold_w(int field, const void *w1_dev, const void *w2_dev, size_t n, const void *r_host, void *out_dev,
+                int device, void *stream);
+/* E part (src/plonk/mod.rs:1118-1131): out[i] = e[i] + sum_{k<n_terms} r^(k+1) * terms[k][i].
+ * terms_dev: HOST array of n_terms device pointers (the cross-term vectors T_1..T_d).  n_terms <= 16. */
+int mira_fold_e(int field, const void *e_dev, const void *const *terms_dev, size_t n_terms, size_t n,
+                const void *r_host, void *out_dev, int device, void *stream);
+/* util::concatenate_with_padding (src/util.rs:189-193), the W_i = concat(columns, 2^k) step of
+ * run_sps_protocol_* (src/plonk/mod.rs:682-684): column c (lens[c] elements) followed by zeros up to
+ * pad_size.  *out_len = elements written; fails with MIRA_ERR_INVALID if it exceeds out_capacity. */
+int mira_concat_pad(const void *const *cols_dev, const size_t *lens, size_t n_cols, size_t pad_size, void *out_dev,
+                    size_t out_capacity, size_t *out_len, int device, void *stream);
+
+/* ---- GraphEvaluator (src/polynomial/graph_evaluator.rs:163-388) as a device row program ------------
+ * A program is the serialised `GraphEvaluator { constants, rotations, num_intermediates, calculations }`.
+ * `code` is a sequence of u32 words, one record per `CalculationInfo { calculation, target }` in order:
+ *     word 0 : opcode | (n_operands << 8)     opcode: 0 Add(a,b) 1 Sub(a,b) 2 Mul(a,b) 3 Square(a)
+ *     word 1 : target                                 4 Double(a) 5 Negate(a) 6 Horner(start, factor, parts..)
+ *     then per operand (ValueSource):                 7 Store(a)
+ *     word 0 : kind | (rotation_index << 8)   kind:   0 Constant 1 Intermediate 2 Fixed 3 Poly 4 Challenge
+ *     word 1 : index
+ * Horner's operands are ordered (start_value, factor, parts[0], parts[1], ...).  `constants` are n x 32 B
+ * Montgomery elements (host), `rotations` the i32 rotation table (host).  The result of a row is the value
+ * of the LAST calculation's target (ZERO for an empty program), as GraphEvaluator::evaluate returns. */
+typedef struct mira_eval_program mira_eval_program;
+int mira_eval_program_create(int field, const uint32_t *code, size_t code_words, const void *constants,
+                             size_t n_constants, const int32_t *rotations, size_t n_rotations,
+                             uint32_t num_intermediates, mira_eval_program **out);
+void mira_eval_program_destroy(mira_eval_program *prog);
+
+/* PlonkEvalDomain (src/plonk/eval.rs:93-106).  The pointer ARRAYS and `challenges` live on the host; the
+ * columns they point to live on the device.  Poly{index} operands are resolved exactly as
+ * GetDataForEval::eval_column_var (src/plonk/eval.rs:57-70: selectors, then fixed, then advice) and
+ * PlonkEvalDomain::eval_advice_var (src/plonk/eval.rs:153-228: W1s / W2s, lookup sub-columns). */
+typedef struct {
+  uint64_t row_size;            /* GetDataForEval::row_size() */
+  uint32_t num_selectors, num_fixed, num_advice, num_lookup, num_challenges, num_w1, num_w2, _pad;
+  const void *const *selectors; /* [num_selectors] -> row_size bytes, Rust Vec<bool> image (0 / 1) */
+  const void *const *fixed;     /* [num_fixed]     -> row_size x 32 B */
+  const void *const *w1;        /* W1s[i] */
+  const uint64_t *w1_len;       /* W1s[i].len() in elements */
+  const void *const *w2;        /* W2s[i] */
+  const uint64_t *w2_len;
+  const void *challenges;       /* num_challenges x 32 B: U1.challenges | U1.u | U2.challenges | 1
+                                   (src/nifs/vanilla/mod.rs:91) */
+} mira_eval_domain;
+
+/* out_dev[row] = evaluator.evaluate(&domain, row) for row in [0, row_size)
+ * (the `(0..row_size).into_par_iter().map(..)` of src/nifs/vanilla/mod.rs:109-116).
+ * Index errors the reference raises per row are raised here once, when the program is bound to the domain. */
+int mira_eval_rows(const mira_eval_program *prog, const mira_eval_domain *dom, void *out_dev, int device,
+                   void *stream);
+typedef struct {
+  uint32_t instructions;   /* device instructions after Store-forwarding and Horner expansion */
+  uint32_t slots;          /* live intermediates kept per row (local memory) */
+  uint32_t accesses;       /* distinct (column, rotation) loads */
+  uint32_t uniforms;       /* constants + challenges */
+  uint32_t muls, adds;     /* field multiplications (incl. squarings) / additive ops per row */
+  uint32_t loads;          /* column loads executed per row */
+  uint32_t _pad;
+} mira_eval_stats;
+/* statistics of the last mira_eval_rows binding of this program */
+int mira_eval_program_stats(const mira_eval_program *prog, mira_eval_stats *out);
+
+/* ---- fft::best_fft (src/fft.rs:51-115): in-place radix-2 transform of 2^log_n elements ------------
+ * omega_host: 32 B element of multiplicative order 2^log_n (host).  Output order and values are those of
+ * the reference: bit-reversal permutation, then log_n butterfly stages with twiddles omega^i. */
+int mira_fft(int field, void *a_dev, uint32_t log_n, const void *omega_host, int device, void *stream);
+/* fft (inverse = 0, src/fft.rs:160-162) / ifft (inverse = 1, src/fft.rs:165-175, including the division
+ * by 2^log_n): omega = get_omega_or_inv(log_n) derived on the device from PrimeField::ROOT_OF_UNITY.
+ * Only MIRA_FR has a usable 2-adic subgroup (S = 28); log_n > S fails with MIRA_ERR_INVALID as the
+ * reference's assert does. */
+int mira_fft_std(int field, void *a_dev, uint32_t log_n, int inverse, int device, void *stream);
+
 /* ---- device-side synthetic inputs and unit-test hooks ---------------------------------------------
  * Deterministic generators shared bit-for-bit with oracle/mira_oracle.c (oracle_gen_scalars /
  * oracle_gen_bases) so that bench.py can build 2^24..2^26-point keys on the GPU in seconds.
@@ -105,6 +192,15 @@ int mira_test_field_op(int field, int op, const void *a, const void *b, size_t n
 /* Element-wise group kernels over HOST arrays of n 64-byte affine points.
  * op: 0 p+q via XYZZ mixed add, 1 p+q via XYZZ full add, 2 2p, 3 k*p with k = (uint32) first word of q */
 int mira_test_point_op(int curve, int op, const void *p, const void *q, size_t n, int device, void *out);
+
+/* Host-only unit-test hook: binds `prog` to `dom` (pointers are only recorded, never dereferenced) and returns
+ * the linked device program, so the CPU test-suite can check the linker (Store forwarding, Horner expansion,
+ * liveness-based slot allocation) without a GPU.  instr_words: 4 u32 per device instruction
+ * (op | akind << 4 | bkind << 8 | dst << 16, a, b, 0; kinds 0 slot, 1 uniform, 2 access); access_words: 3 u64 per
+ * access (column pointer, rotation as i64, is_selector).  Uniform i is constants[i], then the challenges, then ZERO. */
+int mira_test_eval_link(const mira_eval_program *prog, const mira_eval_domain *dom, uint32_t *instr_words,
+                        size_t instr_cap, size_t *n_instr, uint64_t *access_words, size_t access_cap, size_t *n_access,
+                        uint32_t *result_kind, uint32_t *result_idx, uint32_t *n_slots);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,12 @@ MIRA_ERR_TOO_LONG_INPUT = -1
 MIRA_ERR_CUDA = -2
 MIRA_ERR_INVALID = -3
 MIRA_ERR_NOT_ON_CURVE = -4
+MIRA_ERR_EVAL_CHALLENGE = -11
+MIRA_ERR_EVAL_COLUMN = -12
+MIRA_ERR_EVAL_ROW = -13
+MIRA_ERR_EVAL_WITNESS_INDEX = -14
+MIRA_ERR_EVAL_PROGRAM = -15
+MIRA_FQ, MIRA_FR = 0, 1
 
 # every symbol include/mira_b200.h declares (tests/test_capi_symbols.py checks the .so exports them all)
 SYMBOLS = [
@@ -21,7 +27,25 @@ SYMBOLS = [
     "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_commit", "mira_msm_commit_device",
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
+    "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
+    "mira_eval_rows", "mira_eval_program_stats", "mira_fft", "mira_fft_std", "mira_test_eval_link",
 ]
+_VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy")
+
+
+class EvalDomain(C.Structure):
+    """mira_eval_domain (include/mira_b200.h) == PlonkEvalDomain (src/plonk/eval.rs:93-106)."""
+    _fields_ = [("row_size", C.c_uint64), ("num_selectors", C.c_uint32), ("num_fixed", C.c_uint32),
+                ("num_advice", C.c_uint32), ("num_lookup", C.c_uint32), ("num_challenges", C.c_uint32),
+                ("num_w1", C.c_uint32), ("num_w2", C.c_uint32), ("_pad", C.c_uint32),
+                ("selectors", C.c_void_p), ("fixed", C.c_void_p), ("w1", C.c_void_p), ("w1_len", C.c_void_p),
+                ("w2", C.c_void_p), ("w2_len", C.c_void_p), ("challenges", C.c_void_p)]
+
+
+class EvalStats(C.Structure):
+    _fields_ = [("instructions", C.c_uint32), ("slots", C.c_uint32), ("accesses", C.c_uint32), ("uniforms", C.c_uint32),
+                ("muls", C.c_uint32), ("adds", C.c_uint32), ("loads", C.c_uint32), ("_pad", C.c_uint32)]
+
 
 
 class MsmStats(C.Structure):
@@ -69,8 +93,20 @@ def lib():
     L.mira_gen_bases.argtypes = [i, u64, sz, sz, i, vp]
     L.mira_test_field_op.argtypes = [i, i, vp, vp, sz, i, vp]
     L.mira_test_point_op.argtypes = [i, i, vp, vp, sz, i, vp]
+    L.mira_fold_w.argtypes = [i, vp, vp, sz, vp, vp, i, vp]
+    L.mira_fold_e.argtypes = [i, vp, vp, sz, sz, vp, vp, i, vp]
+    L.mira_concat_pad.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(sz), i, vp]
+    L.mira_eval_program_create.argtypes = [i, vp, sz, vp, sz, vp, sz, C.c_uint32, C.POINTER(vp)]
+    L.mira_eval_program_destroy.argtypes = [vp]
+    L.mira_eval_program_destroy.restype = None
+    L.mira_eval_rows.argtypes = [vp, C.POINTER(EvalDomain), vp, i, vp]
+    L.mira_eval_program_stats.argtypes = [vp, C.POINTER(EvalStats)]
+    u32p = C.POINTER(C.c_uint32)
+    L.mira_test_eval_link.argtypes = [vp, C.POINTER(EvalDomain), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), u32p, u32p, u32p]
+    L.mira_fft.argtypes = [i, vp, C.c_uint32, vp, i, vp]
+    L.mira_fft_std.argtypes = [i, vp, C.c_uint32, i, i, vp]
     for name in SYMBOLS:
-        if name not in ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len"):
+        if name not in _VOID:
             getattr(L, name).restype = i
     _LIB = L
     return L

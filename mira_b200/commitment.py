@@ -75,6 +75,8 @@ class CommitmentKey:
         self.curve = curve
         self.device = device
         self._n = n
+        self._image = bases          # the memory image of `ck: Box<[C]>` this key was made from (for save_to_file)
+        self._image_on_device = on_device
         self._ctx = C.c_void_p()
         _check(L.mira_msm_ctx_create(curve, ptr, n, 1 if on_device else 0, device, C.byref(self._ctx)))
 
@@ -141,7 +143,16 @@ class CommitmentKey:
         return cls(curve, buf, device, on_device=True)
 
     def save_to_file(self, file_path: str):
-        raise NotImplementedError("keys are saved from the host copy; see CommitmentKey.setup / tests")
+        """Writes the key as the raw memory image of `[C]`, 64 bytes per point (src/commitment.rs:96-107)."""
+        if self._image is None:
+            data = b""
+        elif self._image_on_device:
+            data = self._image.cpu().numpy().tobytes()[: self._n * POINT_BYTES]
+        else:
+            ptr, nbytes, keep = _as_ptr(self._image)
+            data = C.string_at(ptr, self._n * POINT_BYTES)
+        with open(file_path, "wb") as f:
+            f.write(data)
 
     # -- extensions used by the GPU pipeline ------------------------------------------------------
     def check_on_curve(self):

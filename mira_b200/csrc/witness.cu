@@ -1,0 +1,754 @@
+// witness.cu — the witness side of the hot path in HBM: cross-term row evaluator, fold AXPY, column
+// concatenation and radix-2 FFT, plus their C ABI (include/mira_b200.h, "field vectors in HBM").
+//
+// Replaces, on the device:
+//   GraphEvaluator::evaluate under into_par_iter   /root/reference/src/nifs/vanilla/mod.rs:100-121,
+//                                                   src/polynomial/graph_evaluator.rs:93-149,361-388,
+//                                                   src/plonk/eval.rs:57-70,153-228
+//   RelaxedPlonkWitness::fold                       src/plonk/mod.rs:1097-1134
+//   concatenate_with_padding                        src/util.rs:189-193
+//   best_fft / fft / ifft                           src/fft.rs:12-27,51-115,160-175
+// Outputs stay in HBM so they feed mira_msm_commit_device without crossing PCIe.
+#include <algorithm>
+#include <map>
+
+#include "ctx.hpp"
+#include "field.cuh"
+
+namespace mira {
+
+// ------------------------------------------------------------------ fold
+// One thread per element, 128-bit loads/stores; HBM-bound: 96 B per element for W (two reads, one write),
+// (n_terms + 2) * 32 B per element for E.
+template <class F>
+__global__ void __launch_bounds__(256) k_fold_w(const void* __restrict__ w1, const void* __restrict__ w2, size_t n, Fe<F> r,
+                                                void* __restrict__ out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fe<F> a = fe_load<F>(reinterpret_cast<const char*>(w1) + i * 32);
+    Fe<F> b = fe_load<F>(reinterpret_cast<const char*>(w2) + i * 32);
+    fe_store<F>(reinterpret_cast<char*>(out) + i * 32, fe_add(a, fe_mul(r, b)));
+  }
+}
+
+constexpr int MAX_FOLD_TERMS = 16;
+struct FoldTerms {
+  const void* t[MAX_FOLD_TERMS];
+};
+// powers r^1..r^n_terms are computed once per block into shared memory (n_terms sequential products)
+template <class F>
+__global__ void __launch_bounds__(256) k_fold_e(const void* __restrict__ e, FoldTerms terms, int n_terms, size_t n, Fe<F> r,
+                                                void* __restrict__ out) {
+  __shared__ uint32_t pw[MAX_FOLD_TERMS][8];
+  if (threadIdx.x == 0) {
+    Fe<F> p = r;
+    for (int k = 0; k < n_terms; k++) {
+      for (int j = 0; j < 8; j++) pw[k][j] = p.v[j];
+      p = fe_mul(p, r);
+    }
+  }
+  __syncthreads();
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fe<F> acc = fe_load<F>(reinterpret_cast<const char*>(e) + i * 32);
+    for (int k = 0; k < n_terms; k++) {
+      Fe<F> p;
+#pragma unroll
+      for (int j = 0; j < 8; j++) p.v[j] = pw[k][j];
+      Fe<F> t = fe_load<F>(reinterpret_cast<const char*>(terms.t[k]) + i * 32);
+      acc = fe_add(acc, fe_mul(p, t));
+    }
+    fe_store<F>(reinterpret_cast<char*>(out) + i * 32, acc);
+  }
+}
+
+// ------------------------------------------------------------------ row evaluator
+// Device instruction (16 B): x = op | akind << 4 | bkind << 8 | dst << 16, y = a, z = b.
+enum : uint32_t { DOP_ADD = 0, DOP_SUB, DOP_MUL, DOP_SQUARE, DOP_DOUBLE, DOP_NEGATE, DOP_COPY };
+enum : uint32_t { DK_SLOT = 0, DK_UNIFORM = 1, DK_ACCESS = 2 };
+struct Access {          // one distinct (column, rotation) load
+  const void* ptr;       // column base (32 B elements, or 1 B selectors)
+  int32_t rot;
+  uint32_t is_selector;
+};
+
+template <class F, int S>
+__device__ __forceinline__ Fe<F> ev_fetch(uint32_t kind, uint32_t idx, const Fe<F>* slots, const void* __restrict__ uniforms,
+                                          const Access* __restrict__ acc, uint64_t row, uint64_t row_size) {
+  if (kind == DK_SLOT) return slots[idx];
+  if (kind == DK_UNIFORM) return fe_load<F>(reinterpret_cast<const char*>(uniforms) + (size_t)idx * 32);
+  Access a = acc[idx];
+  uint64_t r = row;
+  if (a.rot) {                       // get_rotation_idx: (row + rot).rem_euclid(row_size)
+    int64_t v = ((int64_t)row + a.rot) % (int64_t)row_size;
+    r = (uint64_t)(v < 0 ? v + (int64_t)row_size : v);
+  }
+  if (a.is_selector) return reinterpret_cast<const uint8_t*>(a.ptr)[r] ? fe_one<F>() : fe_zero<F>();
+  return fe_load<F>(reinterpret_cast<const char*>(a.ptr) + r * 32);
+}
+
+// One thread per row (grid-stride).  The linked program sits in shared memory and is warp-uniform, so the
+// opcode switch never diverges; live intermediates sit in a per-thread local array (L1-resident for the slot
+// counts the linker produces).  Integer-pipe bound: ~1 Montgomery product per MUL/SQUARE instruction.
+template <class F, int S>
+__global__ void __launch_bounds__(128) k_eval_rows(const uint4* __restrict__ prog, uint32_t n_instr, const void* __restrict__ uniforms,
+                                                   const Access* __restrict__ acc, uint32_t out_kind, uint32_t out_idx,
+                                                   uint64_t row_size, void* __restrict__ out) {
+  extern __shared__ uint4 s_prog[];
+  for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) s_prog[i] = prog[i];
+  __syncthreads();
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_size; row += stride) {
+    Fe<F> slots[S];
+    for (uint32_t pc = 0; pc < n_instr; pc++) {
+      uint4 ins = s_prog[pc];
+      uint32_t op = ins.x & 0xf, ak = (ins.x >> 4) & 0xf, bk = (ins.x >> 8) & 0xf, dst = ins.x >> 16;
+      Fe<F> a = ev_fetch<F, S>(ak, ins.y, slots, uniforms, acc, row, row_size);
+      Fe<F> r;
+      if (op <= DOP_MUL) {
+        Fe<F> b = ev_fetch<F, S>(bk, ins.z, slots, uniforms, acc, row, row_size);
+        if (op == DOP_MUL) r = fe_mul(a, b);
+        else if (op == DOP_ADD) r = fe_add(a, b);
+        else r = fe_sub(a, b);
+      } else if (op == DOP_SQUARE) r = fe_sqr(a);
+      else if (op == DOP_DOUBLE) r = fe_dbl(a);
+      else if (op == DOP_NEGATE) r = fe_neg(a);
+      else r = a;
+      slots[dst] = r;
+    }
+    Fe<F> res = ev_fetch<F, S>(out_kind, out_idx, slots, uniforms, acc, row, row_size);
+    fe_store<F>(reinterpret_cast<char*>(out) + row * 32, res);
+  }
+}
+
+// ------------------------------------------------------------------ FFT
+// consts[0] = omega, consts[1] = scale (ifft divisor) — derived on the device for the fft/ifft wrappers.
+template <class F>
+__global__ void k_fft_consts(uint32_t k, int inverse, void* consts) {
+  if (threadIdx.x || blockIdx.x) return;
+  // PrimeField::ROOT_OF_UNITY of bn256::Fr, S = 28 (7^((r-1)/2^28)); validated by src/fft.rs:239-258
+  Fe<F> c;
+  const uint32_t root[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du, 0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+  for (int i = 0; i < 8; i++) c.v[i] = root[i];
+  Fe<F> w = fe_from_canonical(c);
+  if (inverse) w = fe_inv(w);
+  for (uint32_t i = k; i < 28; i++) w = fe_sqr(w);
+  Fe<F> two = fe_add(fe_one<F>(), fe_one<F>());
+  Fe<F> inv2 = fe_inv(two), d = fe_one<F>();
+  for (uint32_t i = 0; i < k; i++) d = fe_mul(d, inv2);
+  fe_store<F>(consts, w);
+  fe_store<F>(reinterpret_cast<char*>(consts) + 32, d);
+}
+
+// tw[i] = omega^i, i < half (square-and-multiply per thread: exact, so equal to the reference's running product)
+template <class F>
+__global__ void __launch_bounds__(256) k_fft_twiddles(const void* __restrict__ consts, size_t half, void* __restrict__ tw) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  Fe<F> base = fe_load<F>(consts), acc = fe_one<F>();
+  for (size_t e = i; e; e >>= 1) {
+    if (e & 1) acc = fe_mul(acc, base);
+    base = fe_sqr(base);
+  }
+  fe_store<F>(reinterpret_cast<char*>(tw) + i * 32, acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_fft_bitrev(void* a, uint32_t log_n) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ((size_t)1 << log_n)) return;
+  size_t rk = (size_t)(__brevll((unsigned long long)k) >> (64 - log_n));
+  if (log_n == 0) rk = 0;
+  if (k < rk) {
+    char* p = reinterpret_cast<char*>(a);
+    const uint4* pk = reinterpret_cast<const uint4*>(p + k * 32);
+    const uint4* pr = reinterpret_cast<const uint4*>(p + rk * 32);
+    uint4 k0 = pk[0], k1 = pk[1], r0 = pr[0], r1 = pr[1];
+    reinterpret_cast<uint4*>(p + k * 32)[0] = r0; reinterpret_cast<uint4*>(p + k * 32)[1] = r1;
+    reinterpret_cast<uint4*>(p + rk * 32)[0] = k0; reinterpret_cast<uint4*>(p + rk * 32)[1] = k1;
+  }
+}
+
+// Stages [0, stages) fused in shared memory on tiles of 2^stages consecutive (already bit-reversed) elements.
+constexpr int FFT_TILE_LOG = 10;
+template <class F>
+__global__ void __launch_bounds__(512) k_fft_tile(void* a, uint32_t log_n, uint32_t stages, const void* __restrict__ tw) {
+  extern __shared__ uint4 sm_fft[];
+  const size_t tile = (size_t)1 << stages, base = (size_t)blockIdx.x * tile;
+  char* g = reinterpret_cast<char*>(a) + base * 32;
+  for (size_t i = threadIdx.x; i < tile * 2; i += blockDim.x) sm_fft[i] = reinterpret_cast<const uint4*>(g)[i];
+  __syncthreads();
+  const size_t n = (size_t)1 << log_n;
+  for (uint32_t s = 0; s < stages; s++) {
+    size_t half = (size_t)1 << s, twiddle_chunk = n >> (s + 1);
+    for (size_t t = threadIdx.x; t < tile / 2; t += blockDim.x) {
+      size_t i = t & (half - 1), left = ((t >> s) << (s + 1)) + i, right = left + half;
+      Fe<F> l, r;
+      {
+        uint4 lo = sm_fft[2 * left], hi = sm_fft[2 * left + 1];
+        l.v[0] = lo.x; l.v[1] = lo.y; l.v[2] = lo.z; l.v[3] = lo.w; l.v[4] = hi.x; l.v[5] = hi.y; l.v[6] = hi.z; l.v[7] = hi.w;
+        lo = sm_fft[2 * right]; hi = sm_fft[2 * right + 1];
+        r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+      }
+      if (i) r = fe_mul(r, fe_load<F>(reinterpret_cast<const char*>(tw) + (i * twiddle_chunk) * 32));
+      Fe<F> x = fe_add(l, r), y = fe_sub(l, r);
+      sm_fft[2 * left] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]); sm_fft[2 * left + 1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+      sm_fft[2 * right] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]); sm_fft[2 * right + 1] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+    }
+    __syncthreads();
+  }
+  for (size_t i = threadIdx.x; i < tile * 2; i += blockDim.x) reinterpret_cast<uint4*>(g)[i] = sm_fft[i];
+}
+
+// One butterfly stage straight on HBM (stages >= FFT_TILE_LOG): 64 B read + 64 B written per butterfly.
+template <class F>
+__global__ void __launch_bounds__(256) k_fft_stage(void* a, uint32_t log_n, uint32_t s, const void* __restrict__ tw) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)1 << log_n;
+  if (t >= n / 2) return;
+  size_t half = (size_t)1 << s, i = t & (half - 1), left = ((t >> s) << (s + 1)) + i, right = left + half;
+  char* p = reinterpret_cast<char*>(a);
+  Fe<F> l = fe_load<F>(p + left * 32), r = fe_load<F>(p + right * 32);
+  if (i) r = fe_mul(r, fe_load<F>(reinterpret_cast<const char*>(tw) + (i * (n >> (s + 1))) * 32));
+  fe_store<F>(p + left * 32, fe_add(l, r));
+  fe_store<F>(p + right * 32, fe_sub(l, r));
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_scale(void* a, size_t n, const void* __restrict__ scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<F> d = fe_load<F>(scale);
+  char* p = reinterpret_cast<char*>(a) + i * 32;
+  fe_store<F>(p, fe_mul(fe_load<F>(p), d));
+}
+
+}  // namespace mira
+
+// =================================================================================== host side
+struct mira_eval_program {
+  int field = 0;
+  std::vector<uint32_t> code;
+  std::vector<uint8_t> constants;     // n x 32 B
+  std::vector<int32_t> rotations;
+  uint32_t num_intermediates = 0;
+  mira_eval_stats stats{};
+  // device copies of the last binding (re-used when the same domain pointers come back)
+  mira_host::DevBuf d_prog, d_uniforms, d_access;
+  int device = -1;
+};
+
+namespace mira_host {
+using namespace mira;
+
+static int set_device(int device) {
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(MIRA_ERR_CUDA, "CUDA device %d not available (%d visible)", device, count);
+  CU(cudaSetDevice(device));
+  return MIRA_OK;
+}
+static int valid_field(int f) { return f == MIRA_FQ || f == MIRA_FR; }
+static unsigned grid_for(size_t n, int threads, int per_sm) {
+  size_t want = (n + threads - 1) / threads, cap = (size_t)148 * per_sm;
+  return (unsigned)std::max<size_t>(1, std::min(want, cap));
+}
+
+template <class F> static Fe<F> fe_from_host(const void* p) {
+  Fe<F> r;
+  memcpy(r.v, p, 32);
+  return r;
+}
+
+template <class F>
+static int fold_w_impl(const void* w1, const void* w2, size_t n, const void* r, void* out, cudaStream_t st) {
+  if (!n) return MIRA_OK;
+  k_fold_w<F><<<grid_for(n, 256, 8), 256, 0, st>>>(w1, w2, n, fe_from_host<F>(r), out);
+  CU(cudaGetLastError());
+  return MIRA_OK;
+}
+template <class F>
+static int fold_e_impl(const void* e, const void* const* terms, size_t n_terms, size_t n, const void* r, void* out, cudaStream_t st) {
+  if (!n) return MIRA_OK;
+  FoldTerms ft{};
+  for (size_t k = 0; k < n_terms; k++) ft.t[k] = terms[k];
+  k_fold_e<F><<<grid_for(n, 256, 8), 256, 0, st>>>(e, ft, (int)n_terms, n, fe_from_host<F>(r), out);
+  CU(cudaGetLastError());
+  return MIRA_OK;
+}
+
+// ---- linker: GraphEvaluator program + PlonkEvalDomain -> device instructions ---------------------
+struct Opnd {
+  uint32_t kind, idx;   // DK_*
+  bool operator==(const Opnd& o) const { return kind == o.kind && idx == o.idx; }
+};
+struct LInstr {
+  uint32_t op;
+  int32_t dst_var;      // variable (intermediate id) defined
+  Opnd a, b;
+};
+
+struct Linker {
+  const mira_eval_program& P;
+  const mira_eval_domain& D;
+  std::vector<Access> access;
+  std::map<std::pair<const void*, int32_t>, uint32_t> access_ix;
+  Linker(const mira_eval_program& p, const mira_eval_domain& d) : P(p), D(d) {}
+
+  uint32_t add_access(const void* ptr, int32_t rot, bool sel) {
+    auto key = std::make_pair(ptr, rot);
+    auto it = access_ix.find(key);
+    if (it != access_ix.end()) return it->second;
+    access.push_back(Access{ptr, rot, sel ? 1u : 0u});
+    access_ix[key] = (uint32_t)access.size() - 1;
+    return (uint32_t)access.size() - 1;
+  }
+  // PlonkEvalDomain::eval_advice_var (src/plonk/eval.rs:153-228); row-independent part, bounds for the last row
+  int advice(size_t index, int32_t rot, Opnd* out) {
+    size_t row_size = D.row_size, num_advice = D.num_advice, num_lookup = D.num_lookup;
+    size_t max_width = num_advice + num_lookup * 5;
+    bool first = index < max_width;
+    if (!first) index -= max_width;
+    size_t num_witness = first ? D.num_w1 : D.num_w2, i, j;
+    if (index < num_advice) {
+      i = 0; j = index;
+    } else {
+      size_t li = (index - num_advice) / 5, ls = (index - num_advice) % 5;
+      bool first_round = ls < 3;
+      if (!first_round) ls -= 3;
+      if (num_witness == 2) {
+        if (first_round) { i = 0; j = num_advice + li * 3 + ls; } else { i = 1; j = li * 2 + ls; }
+      } else if (num_witness == 3) {
+        if (first_round) { i = 1; j = li * 3 + ls; } else { i = 2; j = li * 2 + ls; }
+      } else {
+        return fail(MIRA_ERR_EVAL_WITNESS_INDEX, "Invalid witness index. num_witness: %zu, num_advice: %zu, num_lookup: %zu, index: %zu",
+                    num_witness, num_advice, num_lookup, index);
+      }
+    }
+    const void* const* W = first ? D.w1 : D.w2;
+    const uint64_t* L = first ? D.w1_len : D.w2_len;
+    if (num_witness <= i || L[i] < (j + 1) * row_size)
+      return fail(MIRA_ERR_EVAL_WITNESS_INDEX, "Invalid witness index. num_witness: %zu, num_advice: %zu, num_lookup: %zu, index: %zu",
+                  num_witness, num_advice, num_lookup, index);
+    *out = Opnd{DK_ACCESS, add_access(reinterpret_cast<const char*>(W[i]) + j * row_size * 32, rot, false)};
+    return MIRA_OK;
+  }
+  // the get_value closure of Calculation::evaluate (graph_evaluator.rs:101-131); intermediates stay symbolic
+  int value(const uint32_t* o, Opnd* out, int32_t* var) {
+    uint32_t kind = o[0] & 0xff, rix = o[0] >> 8, index = o[1];
+    *var = -1;
+    switch (kind) {
+      case 0:
+        if (index >= P.constants.size() / 32) return fail(MIRA_ERR_EVAL_PROGRAM, "constant index %u out of range", index);
+        *out = Opnd{DK_UNIFORM, index};
+        return MIRA_OK;
+      case 1:
+        if (index >= P.num_intermediates) return fail(MIRA_ERR_EVAL_PROGRAM, "intermediate index %u out of range", index);
+        *var = (int32_t)index;
+        *out = Opnd{DK_SLOT, index};
+        return MIRA_OK;
+      case 2:
+        if (index >= D.num_fixed) return fail(MIRA_ERR_EVAL_COLUMN, "column variable index out of boundary: %u", index);
+        if (rix >= P.rotations.size()) return fail(MIRA_ERR_EVAL_PROGRAM, "rotation index %u out of range", rix);
+        *out = Opnd{DK_ACCESS, add_access(D.fixed[index], P.rotations[rix], false)};
+        return MIRA_OK;
+      case 3: {
+        if (rix >= P.rotations.size()) return fail(MIRA_ERR_EVAL_PROGRAM, "rotation index %u out of range", rix);
+        int32_t rot = P.rotations[rix];
+        if (index < D.num_selectors) {       // eval_column_var: selectors, then fixed, then advice
+          *out = Opnd{DK_ACCESS, add_access(D.selectors[index], rot, true)};
+          return MIRA_OK;
+        }
+        if (index - D.num_selectors < D.num_fixed) {
+          *out = Opnd{DK_ACCESS, add_access(D.fixed[index - D.num_selectors], rot, false)};
+          return MIRA_OK;
+        }
+        return advice((size_t)index - D.num_selectors - D.num_fixed, rot, out);
+      }
+      case 4:
+        if (index >= D.num_challenges)
+          return fail(MIRA_ERR_EVAL_CHALLENGE, "challenge index out of boundary: %u (len %u)", index, D.num_challenges);
+        *out = Opnd{DK_UNIFORM, (uint32_t)(P.constants.size() / 32) + index};
+        return MIRA_OK;
+    }
+    return fail(MIRA_ERR_EVAL_PROGRAM, "unknown value source kind %u", kind);
+  }
+};
+
+static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::vector<uint4>* out_prog, std::vector<Access>* out_access,
+                        Opnd* out_result, uint32_t* out_slots) {
+  Linker L(*P, *D);
+  std::vector<LInstr> ins;
+  const std::vector<uint32_t>& code = P->code;
+  const uint32_t NV = P->num_intermediates;
+  // pass 1: decode; are targets unique (the form GraphEvaluator::add_calculation produces)?
+  std::vector<int> defs(NV, 0);
+  for (size_t pc = 0; pc < code.size();) {
+    if (pc + 2 > code.size()) return fail(MIRA_ERR_EVAL_PROGRAM, "truncated program");
+    uint32_t nops = code[pc] >> 8, target = code[pc + 1];
+    if (pc + 2 + 2 * (size_t)nops > code.size() || target >= NV) return fail(MIRA_ERR_EVAL_PROGRAM, "malformed record at word %zu", pc);
+    defs[target]++;
+    pc += 2 + 2 * (size_t)nops;
+  }
+  bool ssa = true;
+  for (uint32_t v = 0; v < NV; v++) ssa = ssa && defs[v] <= 1;
+  // pass 2: resolve operands; forward Store(x) (x not an intermediate, or any x when targets are unique)
+  std::vector<Opnd> alias(NV, Opnd{DK_SLOT, 0});
+  std::vector<char> aliased(NV, 0);
+  int32_t last_target = -1;
+  P->stats = mira_eval_stats{};
+  auto resolve = [&](const uint32_t* o, Opnd* r) -> int {
+    int32_t var;
+    int rc = L.value(o, r, &var);
+    if (rc) return rc;
+    if (var >= 0 && aliased[var]) *r = alias[var];
+    return MIRA_OK;
+  };
+  for (size_t pc = 0; pc < code.size();) {
+    uint32_t op = code[pc] & 0xff, nops = code[pc] >> 8, target = code[pc + 1];
+    const uint32_t* o = &code[pc + 2];
+    int rc;
+    Opnd a{}, b{};
+    last_target = (int32_t)target;
+    switch (op) {
+      case 0: case 1: case 2:
+        if (nops != 2) return fail(MIRA_ERR_EVAL_PROGRAM, "binary op with %u operands", nops);
+        if ((rc = resolve(o, &a)) || (rc = resolve(o + 2, &b))) return rc;
+        ins.push_back(LInstr{op == 0 ? DOP_ADD : op == 1 ? DOP_SUB : DOP_MUL, (int32_t)target, a, b});
+        aliased[target] = 0;
+        break;
+      case 3: case 4: case 5:
+        if (nops != 1) return fail(MIRA_ERR_EVAL_PROGRAM, "unary op with %u operands", nops);
+        if ((rc = resolve(o, &a))) return rc;
+        ins.push_back(LInstr{op == 3 ? DOP_SQUARE : op == 4 ? DOP_DOUBLE : DOP_NEGATE, (int32_t)target, a, a});
+        aliased[target] = 0;
+        break;
+      case 7:
+        if (nops != 1) return fail(MIRA_ERR_EVAL_PROGRAM, "Store with %u operands", nops);
+        if ((rc = resolve(o, &a))) return rc;
+        if (ssa || a.kind != DK_SLOT) {
+          alias[target] = a;
+          aliased[target] = 1;
+        } else {
+          ins.push_back(LInstr{DOP_COPY, (int32_t)target, a, a});
+          aliased[target] = 0;
+        }
+        break;
+      case 6: {   // Horner(start, factor, parts...): value = value * factor + part
+        if (nops < 2) return fail(MIRA_ERR_EVAL_PROGRAM, "Horner with %u operands", nops);
+        Opnd fac{}, cur{};
+        if ((rc = resolve(o + 2, &fac)) || (rc = resolve(o, &cur))) return rc;
+        if (nops == 2) {
+          ins.push_back(LInstr{DOP_COPY, (int32_t)target, cur, cur});
+        } else {
+          for (uint32_t k = 2; k < nops; k++) {
+            Opnd part{};
+            if ((rc = resolve(o + 2 * k, &part))) return rc;
+            ins.push_back(LInstr{DOP_MUL, (int32_t)target, cur, fac});
+            cur = Opnd{DK_SLOT, target};
+            ins.push_back(LInstr{DOP_ADD, (int32_t)target, cur, part});
+          }
+        }
+        aliased[target] = 0;
+        break;
+      }
+      default:
+        return fail(MIRA_ERR_EVAL_PROGRAM, "unknown opcode %u", op);
+    }
+    pc += 2 + 2 * (size_t)nops;
+  }
+  // the uniform table ends with one extra ZERO: the value of an empty program, and of an intermediate that is
+  // read before any calculation wrote it (the reference zero-initialises `intermediates`, graph_evaluator.rs:354-359)
+  const Opnd zero_uniform{DK_UNIFORM, (uint32_t)(P->constants.size() / 32) + D->num_challenges};
+  Opnd result = zero_uniform;
+  bool have_result = last_target >= 0;
+  if (have_result) result = aliased[last_target] ? alias[last_target] : Opnd{DK_SLOT, (uint32_t)last_target};
+  // pass 3: liveness (last read of every variable), dead-code removal, slot allocation
+  const int NI = (int)ins.size();
+  std::vector<int> last_use(NV, -1);
+  std::vector<char> live(NI, 0);
+  {
+    std::vector<char> needed(NV, 0);
+    if (have_result && result.kind == DK_SLOT) needed[result.idx] = 1;
+    for (int i = NI - 1; i >= 0; i--) {
+      LInstr& I = ins[i];
+      if (!needed[I.dst_var]) continue;
+      live[i] = 1;
+      bool self = (I.a.kind == DK_SLOT && (int32_t)I.a.idx == I.dst_var) || (I.b.kind == DK_SLOT && (int32_t)I.b.idx == I.dst_var);
+      if (!self) needed[I.dst_var] = 0;
+      if (I.a.kind == DK_SLOT) needed[I.a.idx] = 1;
+      if (I.b.kind == DK_SLOT) needed[I.b.idx] = 1;
+    }
+  }
+  for (int i = 0; i < NI; i++) {
+    if (!live[i]) continue;
+    if (ins[i].a.kind == DK_SLOT) last_use[ins[i].a.idx] = i;
+    if (ins[i].b.kind == DK_SLOT) last_use[ins[i].b.idx] = i;
+  }
+  if (have_result && result.kind == DK_SLOT) last_use[result.idx] = NI;
+  std::vector<int32_t> slot_of(NV, -1);
+  std::vector<uint32_t> free_slots;
+  uint32_t n_slots = 0;
+  out_prog->clear();
+  for (int i = 0; i < NI; i++) {
+    if (!live[i]) continue;
+    LInstr I = ins[i];
+    auto map_op = [&](Opnd o) -> Opnd {
+      if (o.kind != DK_SLOT) return o;
+      return slot_of[o.idx] >= 0 ? Opnd{DK_SLOT, (uint32_t)slot_of[o.idx]} : zero_uniform;
+    };
+    Opnd a = map_op(I.a), b = map_op(I.b);
+    // operands whose last read is this instruction release their slot before the destination is chosen
+    for (Opnd o : {I.a, I.b})
+      if (o.kind == DK_SLOT && last_use[o.idx] == i && (int32_t)o.idx != I.dst_var && slot_of[o.idx] >= 0) {
+        free_slots.push_back((uint32_t)slot_of[o.idx]);
+        slot_of[o.idx] = -1;
+      }
+    if (slot_of[I.dst_var] < 0) {
+      if (!free_slots.empty()) {
+        slot_of[I.dst_var] = (int32_t)free_slots.back();
+        free_slots.pop_back();
+      } else {
+        slot_of[I.dst_var] = (int32_t)n_slots++;
+      }
+    }
+    uint32_t dst = (uint32_t)slot_of[I.dst_var];
+    if (dst > 0xffff) return fail(MIRA_ERR_EVAL_PROGRAM, "program needs more than 65535 live intermediates");
+    out_prog->push_back(make_uint4(I.op | (a.kind << 4) | (b.kind << 8) | (dst << 16), a.idx, b.idx, 0));
+    if (I.op == DOP_MUL || I.op == DOP_SQUARE) P->stats.muls++;
+    else if (I.op != DOP_COPY) P->stats.adds++;
+    P->stats.loads += (a.kind == DK_ACCESS) + (I.op <= DOP_MUL && b.kind == DK_ACCESS);
+  }
+  if (have_result && result.kind == DK_SLOT) result = slot_of[result.idx] >= 0 ? Opnd{DK_SLOT, (uint32_t)slot_of[result.idx]} : zero_uniform;
+  if (result.kind == DK_ACCESS) P->stats.loads++;
+  *out_access = L.access;
+  *out_result = result;
+  *out_slots = n_slots;
+  P->stats.instructions = (uint32_t)out_prog->size();
+  P->stats.slots = n_slots;
+  P->stats.accesses = (uint32_t)L.access.size();
+  P->stats.uniforms = (uint32_t)(P->constants.size() / 32) + D->num_challenges + 1;
+  return MIRA_OK;
+}
+
+template <class F, int S>
+static int launch_eval(const uint4* prog, uint32_t n_instr, const void* uni, const Access* acc, Opnd res, uint64_t rows, void* out, cudaStream_t st) {
+  size_t smem = (size_t)n_instr * 16;
+  if (smem > 200 * 1024) return fail(MIRA_ERR_EVAL_PROGRAM, "program of %u device instructions does not fit shared memory", n_instr);
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_eval_rows<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_eval_rows<F, S><<<grid_for(rows, 128, 16), 128, smem, st>>>(prog, n_instr, uni, acc, res.kind, res.idx, rows, out);
+  CU(cudaGetLastError());
+  return MIRA_OK;
+}
+
+template <class F>
+static int eval_impl(mira_eval_program* P, const mira_eval_domain* D, void* out, cudaStream_t st) {
+  std::vector<uint4> prog;
+  std::vector<Access> access;
+  Opnd res{};
+  uint32_t slots = 0;
+  int rc = link_program(P, D, &prog, &access, &res, &slots);
+  if (rc) return rc;
+  if (!D->row_size) return MIRA_OK;
+  size_t nconst = P->constants.size(), nuni = nconst + (size_t)D->num_challenges * 32 + 32;   // + the trailing ZERO
+  std::vector<uint8_t> uni(nuni, 0);
+  if (nconst) memcpy(uni.data(), P->constants.data(), nconst);
+  if (D->num_challenges) memcpy(uni.data() + nconst, D->challenges, (size_t)D->num_challenges * 32);
+  if ((rc = P->d_prog.ensure(std::max<size_t>(prog.size(), 1) * 16)) || (rc = P->d_uniforms.ensure(uni.size())) ||
+      (rc = P->d_access.ensure(std::max<size_t>(access.size(), 1) * sizeof(Access))))
+    return rc;
+  // small synchronous uploads (a few KB); the row kernel itself is asynchronous on `st`
+  CU(cudaStreamSynchronize(st));
+  if (!prog.empty()) CU(cudaMemcpy(P->d_prog.p, prog.data(), prog.size() * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(P->d_uniforms.p, uni.data(), uni.size(), cudaMemcpyHostToDevice));
+  if (!access.empty()) CU(cudaMemcpy(P->d_access.p, access.data(), access.size() * sizeof(Access), cudaMemcpyHostToDevice));
+  const uint4* dp = (const uint4*)P->d_prog.p;
+  const Access* da = (const Access*)P->d_access.p;
+  uint32_t ni = (uint32_t)prog.size();
+  if (slots <= 16) return launch_eval<F, 16>(dp, ni, P->d_uniforms.p, da, res, D->row_size, out, st);
+  if (slots <= 64) return launch_eval<F, 64>(dp, ni, P->d_uniforms.p, da, res, D->row_size, out, st);
+  if (slots <= 256) return launch_eval<F, 256>(dp, ni, P->d_uniforms.p, da, res, D->row_size, out, st);
+  return fail(MIRA_ERR_EVAL_PROGRAM, "program keeps %u intermediates live; the device interpreter supports 256", slots);
+}
+
+// ---- FFT -------------------------------------------------------------------------------------------
+template <class F>
+static int fft_impl(void* a, uint32_t log_n, const void* d_consts, bool scale, cudaStream_t st) {
+  const size_t n = (size_t)1 << log_n, half = n / 2;
+  if (log_n == 0) {
+    if (scale) k_scale<F><<<1, 256, 0, st>>>(a, 1, reinterpret_cast<const char*>(d_consts) + 32);
+    CU(cudaGetLastError());
+    return MIRA_OK;
+  }
+  void* tw = nullptr;
+  CU(cudaMallocAsync(&tw, half * 32, st));
+  k_fft_twiddles<F><<<(unsigned)((half + 255) / 256), 256, 0, st>>>(d_consts, half, tw);
+  k_fft_bitrev<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, log_n);
+  uint32_t fused = log_n < (uint32_t)FFT_TILE_LOG ? log_n : (uint32_t)FFT_TILE_LOG;
+  size_t tile = (size_t)1 << fused;
+  k_fft_tile<F><<<(unsigned)(n / tile), 512, tile * 32, st>>>(a, log_n, fused, tw);
+  for (uint32_t s = fused; s < log_n; s++) k_fft_stage<F><<<(unsigned)((half + 255) / 256), 256, 0, st>>>(a, log_n, s, tw);
+  if (scale) k_scale<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, reinterpret_cast<const char*>(d_consts) + 32);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(tw, st);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "fft launch failed: %s", cudaGetErrorString(e));
+  return MIRA_OK;
+}
+
+}  // namespace mira_host
+
+using namespace mira_host;
+
+extern "C" {
+
+int mira_fold_w(int field, const void* w1, const void* w2, size_t n, const void* r, void* out, int device, void* stream) {
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if (!r || (n && (!w1 || !w2 || !out))) return fail(MIRA_ERR_INVALID, "null argument");
+  int rc = set_device(device);
+  if (rc) return rc;
+  return field == MIRA_FQ ? fold_w_impl<mira::FqTag>(w1, w2, n, r, out, (cudaStream_t)stream)
+                          : fold_w_impl<mira::FrTag>(w1, w2, n, r, out, (cudaStream_t)stream);
+}
+
+int mira_fold_e(int field, const void* e, const void* const* terms, size_t n_terms, size_t n, const void* r, void* out, int device,
+                void* stream) {
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if (!r || (n && (!e || !out)) || (n_terms && !terms)) return fail(MIRA_ERR_INVALID, "null argument");
+  if (n_terms > (size_t)mira::MAX_FOLD_TERMS) return fail(MIRA_ERR_INVALID, "at most %d cross terms", mira::MAX_FOLD_TERMS);
+  for (size_t k = 0; k < n_terms; k++)
+    if (n && !terms[k]) return fail(MIRA_ERR_INVALID, "cross term %zu is null", k);
+  int rc = set_device(device);
+  if (rc) return rc;
+  return field == MIRA_FQ ? fold_e_impl<mira::FqTag>(e, terms, n_terms, n, r, out, (cudaStream_t)stream)
+                          : fold_e_impl<mira::FrTag>(e, terms, n_terms, n, r, out, (cudaStream_t)stream);
+}
+
+int mira_concat_pad(const void* const* cols, const size_t* lens, size_t n_cols, size_t pad_size, void* out, size_t cap, size_t* out_len,
+                    int device, void* stream) {
+  if (n_cols && (!cols || !lens)) return fail(MIRA_ERR_INVALID, "null argument");
+  size_t total = 0;
+  for (size_t c = 0; c < n_cols; c++) total += lens[c] > pad_size ? lens[c] : pad_size;
+  if (out_len) *out_len = total;
+  if (total > cap) return fail(MIRA_ERR_INVALID, "concatenation needs %zu elements, output holds %zu", total, cap);
+  if (total && !out) return fail(MIRA_ERR_INVALID, "null output");
+  int rc = set_device(device);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = reinterpret_cast<char*>(out);
+  for (size_t c = 0; c < n_cols; c++) {     // one copy-engine transfer + one memset per column
+    size_t l = lens[c], tot = l > pad_size ? l : pad_size;
+    if (l) CU(cudaMemcpyAsync(w, cols[c], l * 32, cudaMemcpyDeviceToDevice, st));
+    if (tot > l) CU(cudaMemsetAsync(w + l * 32, 0, (tot - l) * 32, st));
+    w += tot * 32;
+  }
+  return MIRA_OK;
+}
+
+int mira_eval_program_create(int field, const uint32_t* code, size_t code_words, const void* constants, size_t n_constants,
+                             const int32_t* rotations, size_t n_rotations, uint32_t num_intermediates, mira_eval_program** out) {
+  if (!out) return fail(MIRA_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if ((code_words && !code) || (n_constants && !constants) || (n_rotations && !rotations)) return fail(MIRA_ERR_INVALID, "null argument");
+  auto* p = new mira_eval_program();
+  p->field = field;
+  p->code.assign(code, code + code_words);
+  p->constants.assign((const uint8_t*)constants, (const uint8_t*)constants + n_constants * 32);
+  p->rotations.assign(rotations, rotations + n_rotations);
+  p->num_intermediates = num_intermediates;
+  *out = p;
+  return MIRA_OK;
+}
+
+void mira_eval_program_destroy(mira_eval_program* p) {
+  if (!p) return;
+  if (p->device >= 0) cudaSetDevice(p->device);
+  p->d_prog.release();
+  p->d_uniforms.release();
+  p->d_access.release();
+  delete p;
+}
+
+int mira_eval_rows(const mira_eval_program* prog, const mira_eval_domain* dom, void* out, int device, void* stream) {
+  if (!prog || !dom) return fail(MIRA_ERR_INVALID, "null argument");
+  if (dom->row_size && !out) return fail(MIRA_ERR_INVALID, "null output");
+  if ((dom->num_selectors && !dom->selectors) || (dom->num_fixed && !dom->fixed) || (dom->num_w1 && (!dom->w1 || !dom->w1_len)) ||
+      (dom->num_w2 && (!dom->w2 || !dom->w2_len)) || (dom->num_challenges && !dom->challenges))
+    return fail(MIRA_ERR_INVALID, "domain has a null column table");
+  if (dom->row_size >= ((uint64_t)1 << 40)) return fail(MIRA_ERR_INVALID, "row_size too large");
+  int rc = set_device(device);
+  if (rc) return rc;
+  auto* p = const_cast<mira_eval_program*>(prog);
+  if (p->device >= 0 && p->device != device) {
+    cudaSetDevice(p->device);
+    p->d_prog.release(); p->d_uniforms.release(); p->d_access.release();
+    cudaSetDevice(device);
+  }
+  p->device = device;
+  return p->field == MIRA_FQ ? eval_impl<mira::FqTag>(p, dom, out, (cudaStream_t)stream)
+                             : eval_impl<mira::FrTag>(p, dom, out, (cudaStream_t)stream);
+}
+
+int mira_test_eval_link(const mira_eval_program* prog, const mira_eval_domain* dom, uint32_t* instr_words, size_t instr_cap,
+                        size_t* n_instr, uint64_t* access_words, size_t access_cap, size_t* n_access, uint32_t* result_kind,
+                        uint32_t* result_idx, uint32_t* n_slots) {
+  if (!prog || !dom || !n_instr || !n_access || !result_kind || !result_idx || !n_slots) return fail(MIRA_ERR_INVALID, "null argument");
+  std::vector<uint4> lp;
+  std::vector<mira::Access> acc;
+  Opnd res{};
+  int rc = link_program(const_cast<mira_eval_program*>(prog), dom, &lp, &acc, &res, n_slots);
+  if (rc) return rc;
+  *n_instr = lp.size();
+  *n_access = acc.size();
+  *result_kind = res.kind;
+  *result_idx = res.idx;
+  if (lp.size() > instr_cap || acc.size() > access_cap) return fail(MIRA_ERR_INVALID, "output buffers too small");
+  for (size_t i = 0; i < lp.size(); i++) {
+    instr_words[4 * i] = lp[i].x; instr_words[4 * i + 1] = lp[i].y; instr_words[4 * i + 2] = lp[i].z; instr_words[4 * i + 3] = lp[i].w;
+  }
+  for (size_t i = 0; i < acc.size(); i++) {
+    access_words[3 * i] = (uint64_t)(uintptr_t)acc[i].ptr;
+    access_words[3 * i + 1] = (uint64_t)(int64_t)acc[i].rot;
+    access_words[3 * i + 2] = acc[i].is_selector;
+  }
+  return MIRA_OK;
+}
+
+int mira_eval_program_stats(const mira_eval_program* prog, mira_eval_stats* out) {
+  if (!prog || !out) return fail(MIRA_ERR_INVALID, "null argument");
+  *out = prog->stats;
+  return MIRA_OK;
+}
+
+int mira_fft(int field, void* a, uint32_t log_n, const void* omega, int device, void* stream) {
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if (!a || !omega) return fail(MIRA_ERR_INVALID, "null argument");
+  if (log_n > 31) return fail(MIRA_ERR_INVALID, "log_n = %u too large", log_n);
+  int rc = set_device(device);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  void* consts = nullptr;
+  CU(cudaMallocAsync(&consts, 64, st));
+  CU(cudaMemcpyAsync(consts, omega, 32, cudaMemcpyHostToDevice, st));
+  rc = field == MIRA_FQ ? fft_impl<mira::FqTag>(a, log_n, consts, false, st) : fft_impl<mira::FrTag>(a, log_n, consts, false, st);
+  cudaFreeAsync(consts, st);
+  return rc;
+}
+
+int mira_fft_std(int field, void* a, uint32_t log_n, int inverse, int device, void* stream) {
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if (!a) return fail(MIRA_ERR_INVALID, "null argument");
+  // get_omega_or_inv's assert (src/fft.rs:13): k <= F::S.  bn256::Fr: S = 28; bn256::Fq: S = 1, no ROOT_OF_UNITY here
+  if (field != MIRA_FR || log_n > 28) return fail(MIRA_ERR_INVALID, "k=%u should no larger than F::S=%d", log_n, field == MIRA_FR ? 28 : 0);
+  int rc = set_device(device);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  void* consts = nullptr;
+  CU(cudaMallocAsync(&consts, 64, st));
+  mira::k_fft_consts<mira::FrTag><<<1, 32, 0, st>>>(log_n, inverse, consts);
+  rc = fft_impl<mira::FrTag>(a, log_n, consts, inverse != 0, st);
+  cudaFreeAsync(consts, st);
+  return rc;
+}
+
+}  // extern "C"

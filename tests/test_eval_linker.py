@@ -1,0 +1,167 @@
+"""CPU-only checks of the host-side linker in mira_b200/csrc/witness.cu (Store forwarding, Horner expansion,
+dead-code removal, liveness-based slot allocation): the linked device program is fetched through the
+`mira_test_eval_link` hook and SIMULATED here in Python with big integers, then compared with the oracle's
+evaluation of the original program.  No compute entry point of the library is called (no GPU here)."""
+import ctypes as C
+import random
+
+import pytest
+
+import graph_evaluator_model as G
+import oracle_lib as O
+import pyref as R
+from witness_util import Domain, mont, pack_program, random_expr, unmont
+
+M = R.R_
+
+
+def _host_domain(d: Domain):
+    """mira_eval_domain whose column pointers are HOST buffers (the linker only records them)."""
+    from mira_b200 import _native as N
+    b = d.as_bytes()
+    keep = []
+
+    def arr(bufs):
+        ks = [C.create_string_buffer(bytes(x), max(len(x), 1)) for x in bufs]
+        keep.extend(ks)
+        a = (C.c_void_p * max(len(ks), 1))(*[C.cast(k, C.c_void_p).value for k in ks])
+        keep.append(a)
+        return a, ks
+    sel, sel_b = arr(b["selectors"])
+    fx, fx_b = arr(b["fixed"])
+    w1, w1_b = arr(b["w1"])
+    w2, w2_b = arr(b["w2"])
+    l1 = (C.c_uint64 * max(len(b["w1"]), 1))(*[len(x) // 32 for x in b["w1"]])
+    l2 = (C.c_uint64 * max(len(b["w2"]), 1))(*[len(x) // 32 for x in b["w2"]])
+    ch = C.create_string_buffer(b["challenges"], max(len(b["challenges"]), 1))
+    keep += [l1, l2, ch]
+    dom = N.EvalDomain(d.row_size, len(b["selectors"]), len(b["fixed"]), d.num_advice, d.num_lookup, len(b["challenges"]) // 32,
+                       len(b["w1"]), len(b["w2"]), 0, C.cast(sel, C.c_void_p), C.cast(fx, C.c_void_p), C.cast(w1, C.c_void_p),
+                       C.cast(l1, C.c_void_p), C.cast(w2, C.c_void_p), C.cast(l2, C.c_void_p), C.cast(ch, C.c_void_p))
+    return dom, keep
+
+
+def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
+    from mira_b200 import _native as N
+    L = N.lib()
+    p = pack_program(ge)
+    h = C.c_void_p()
+    code = (C.c_uint32 * max(len(p["code"]), 1))(*p["code"])
+    rots = (C.c_int32 * max(len(p["rotations"]), 1))(*p["rotations"])
+    assert L.mira_eval_program_create(N.MIRA_FR, code, len(p["code"]), p["constants"], len(p["constants"]) // 32, rots,
+                                      len(p["rotations"]), p["num_intermediates"], C.byref(h)) == 0
+    dom, keep = _host_domain(d)
+    cap = 4096
+    iw = (C.c_uint32 * (4 * cap))()
+    aw = (C.c_uint64 * (3 * cap))()
+    ni, na = C.c_size_t(), C.c_size_t()
+    rk, ri, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = L.mira_test_eval_link(h, C.byref(dom), iw, cap, C.byref(ni), aw, cap, C.byref(na), C.byref(rk), C.byref(ri), C.byref(ns))
+    if rc:
+        L.mira_eval_program_destroy(h)
+        return rc, None, None
+    st = N.EvalStats()
+    L.mira_eval_program_stats(h, C.byref(st))
+    L.mira_eval_program_destroy(h)
+    uniforms = unmont(p["constants"], M) + list(d.challenges) + [0]
+    rows = d.row_size
+
+    def fetch(kind, idx, slots, row):
+        if kind == 0:
+            assert slots[idx] is not None, "slot read before it was written"
+            return slots[idx]
+        if kind == 1:
+            return uniforms[idx]
+        ptr, rot, is_sel = aw[3 * idx], C.c_int64(aw[3 * idx + 1]).value, aw[3 * idx + 2]
+        r = (row + rot) % rows
+        if is_sel:
+            return 1 if C.string_at(ptr + r, 1)[0] else 0
+        return R.from_mont_bytes(C.string_at(ptr + 32 * r, 32), M)
+
+    out = []
+    for row in range(rows):
+        slots = [None] * max(ns.value, 1)
+        for k in range(ni.value):
+            w0, a, b = iw[4 * k], iw[4 * k + 1], iw[4 * k + 2]
+            op, ak, bk, dst = w0 & 0xf, (w0 >> 4) & 0xf, (w0 >> 8) & 0xf, w0 >> 16
+            assert dst < ns.value
+            x = fetch(ak, a, slots, row)
+            if op <= 2:
+                y = fetch(bk, b, slots, row)
+                v = (x + y) if op == 0 else (x - y) if op == 1 else x * y
+            elif op == 3: v = x * x
+            elif op == 4: v = 2 * x
+            elif op == 5: v = -x
+            else: v = x
+            slots[dst] = v % M
+        out.append(fetch(rk.value, ri.value, slots, row))
+    return 0, out, {"instructions": ni.value, "slots": ns.value, "accesses": na.value, "muls": st.muls, "adds": st.adds, "loads": st.loads}
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_linked_random_programs_match_oracle(seed):
+    rng = random.Random(300 + seed)
+    d = Domain(M, 6, 2, 3, 4, 0, 1, 3, seed=seed, sparse=(seed % 2 == 0))
+    for _ in range(6):
+        e = random_expr(rng, M, 2 + 3 + 8, 3, depth=7, rotations=(0, 1, -1, 4))
+        ge = G.GraphEvaluator.new(e, M)
+        rc, out, st = link_and_simulate(ge, d)
+        assert rc == 0
+        assert out == unmont(O.eval_rows(R.FR, pack_program(ge), d.as_bytes()), M) == d.direct(e, range(6))
+        assert st["instructions"] <= len(ge.calculations)
+
+
+@pytest.mark.parametrize("T,n_gates,max_slots", [(5, 1, 16), (5, 2, 64)])
+def test_linked_cross_term_programs(T, n_gates, max_slots):
+    progs, meta = G.cross_term_programs(T, n_gates, M)
+    d = Domain(M, 3, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=55, sparse=True)
+    for p in progs:
+        rc, out, st = link_and_simulate(p, d)
+        assert rc == 0
+        assert out == unmont(O.eval_rows(R.FR, pack_program(p), d.as_bytes()), M)
+        c = p.counts()
+        assert st["muls"] == c["mul"] and st["adds"] == c["add"]        # nothing but Stores is removed
+        assert st["instructions"] == c["mul"] + c["add"]
+        assert st["slots"] <= max_slots, st
+
+
+def test_linker_horner_non_ssa_undefined_and_empty():
+    d = Domain(M, 4, 0, 2, 2, 0, 1, 1, seed=9)
+    K, I, P, CH = G.VS_CONSTANT, G.VS_INTERMEDIATE, G.VS_POLY, G.VS_CHALLENGE
+    ge = G.GraphEvaluator(M)
+    ge.constants += [12345, M - 7]
+    ge.rotations = [0, 1]
+    ge.calculations = [
+        ((G.OP_STORE, (P, 2, 0)), 0),
+        ((G.OP_STORE, (P, 3, 1)), 1),
+        ((G.OP_HORNER, (I, 0, 0), (CH, 0, 0), (I, 1, 0), (K, 3, 0), (P, 0, 0)), 2),
+        ((G.OP_HORNER, (I, 2, 0), (K, 4, 0)), 3),
+        ((G.OP_MUL, (I, 3, 0), (I, 5, 0)), 4),          # intermediate 5 is never written: reads ZERO
+        ((G.OP_ADD, (I, 4, 0), (I, 2, 0)), 2),          # re-defines 2
+        ((G.OP_SQUARE, (I, 2, 0)), 6),
+    ]
+    ge.num_intermediates = 7
+    rc, out, st = link_and_simulate(ge, d)
+    assert rc == 0
+    assert out == unmont(O.eval_rows(R.FR, pack_program(ge), d.as_bytes()), M)
+    empty = G.GraphEvaluator(M)
+    rc, out, st = link_and_simulate(empty, d)
+    assert rc == 0 and out == [0] * 4 and st["instructions"] == 0
+    dead = G.GraphEvaluator(M)                          # a dead calculation before the result is dropped
+    dead.rotations = [0]
+    dead.calculations = [((G.OP_MUL, (P, 2, 0), (P, 3, 0)), 0), ((G.OP_STORE, (P, 1, 0)), 1)]
+    dead.num_intermediates = 2
+    rc, out, st = link_and_simulate(dead, d)
+    assert rc == 0 and st["instructions"] == 0 and out == [d.column(1, r) for r in range(4)]
+
+
+def test_linker_reports_the_reference_errors():
+    from mira_b200 import _native as N
+    d = Domain(M, 4, 0, 1, 2, 0, 1, 1, seed=5)
+    for e, want in ((G.Challenge(1), N.MIRA_ERR_EVAL_CHALLENGE), (G.Polynomial(1 + 4), N.MIRA_ERR_EVAL_WITNESS_INDEX)):
+        rc, _, _ = link_and_simulate(G.GraphEvaluator.new(e, M), d)
+        assert rc == want
+    bad = G.GraphEvaluator(M)
+    bad.calculations = [((G.OP_ADD, (G.VS_CONSTANT, 99, 0), (G.VS_CONSTANT, 0, 0)), 0)]
+    bad.num_intermediates = 1
+    assert link_and_simulate(bad, d)[0] == N.MIRA_ERR_EVAL_PROGRAM

@@ -215,3 +215,50 @@ def test_homomorphism_at_2_20(gpu):
     assert cf == O.point_add(curve, ca, O.scalar_mul(curve, cb, rb))
     k = 1 << 18
     assert ck.commit(a[: 32 * k]) == O.commit(curve, gpu.to_bytes(bases_dev[: 64 * k]), a[: 32 * k])
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_shim_startup_selfcheck(gpu, curve):
+    """The three assertions INTEGRATION.md §3 asks the Rust shim to run once per curve (layout pinning)."""
+    from mira_b200 import CommitmentKey
+    m = R.scalar_mod(curve)
+    g = O.generator(curve)
+    one, zero, minus_one = R.to_mont_bytes(1, m), bytes(32), R.to_mont_bytes(m - 1, m)
+    assert CommitmentKey(curve, g).commit(one) == g
+    assert CommitmentKey(curve, g).commit(zero) == bytes(64)
+    assert CommitmentKey(curve, g + g).commit(minus_one + one) == bytes(64)
+
+
+def test_golden_commit_vectors(gpu):
+    """tests/golden/commit_vectors.json (oracle-generated in the build container): same bytes on the GPU."""
+    import hashlib
+    import json
+    import os
+    from mira_b200 import CommitmentKey
+    with open(os.path.join(os.path.dirname(__file__), "golden", "commit_vectors.json")) as f:
+        vecs = json.load(f)
+    for v in vecs:
+        bases = gpu.to_bytes(gpu.gen_bases_dev(v["curve"], v["seed_bases"], v["n"]))
+        sc = gpu.to_bytes(gpu.gen_scalars_dev(v["curve"], v["seed_scalars"], v["n"], v["dist"]))
+        assert hashlib.sha256(bases).hexdigest() == v["bases_sha256"]
+        assert hashlib.sha256(sc).hexdigest() == v["scalars_sha256"]
+        assert CommitmentKey(v["curve"], bases).commit(sc).hex() == v["commit_hex"]
+
+
+def test_key_file_roundtrip(gpu, tmp_path):
+    """file_tests::consistency (src/commitment.rs:178-194): setup -> save -> load -> same key; plus the
+    on-curve check of load_or_setup_cache (src/commitment.rs:134-156)."""
+    from mira_b200 import BN254_G1, CommitmentKey, NotOnCurve
+    k = 10
+    key = CommitmentKey.load_or_setup_cache(str(tmp_path), "bn256", k, BN254_G1)
+    path = tmp_path / "bn256" / f"{k}.bin"
+    data = path.read_bytes()
+    assert len(data) == 64 << k and all(O.is_on_curve(R.BN254, data[i:i + 64]) for i in range(0, 64 * 32, 64))
+    again = CommitmentKey.load_or_setup_cache(str(tmp_path), "bn256", k, BN254_G1)
+    sc = O.gen_scalars(R.BN254, 99, 1 << k)
+    assert key.commit(sc) == again.commit(sc) == O.commit(R.BN254, data, sc)
+    bad = bytearray(data)
+    bad[64 * 5] ^= 1
+    path.write_bytes(bytes(bad))
+    with pytest.raises(NotOnCurve):
+        CommitmentKey.load_or_setup_cache(str(tmp_path), "bn256", k, BN254_G1)

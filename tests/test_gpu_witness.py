@@ -1,0 +1,311 @@
+"""GPU parity tests for the witness side (cross-term row evaluator, fold, concat, FFT): the CUDA path through the
+C ABI against the CPU oracle on identical bytes — bit-exact.  Run on the B200 box: pytest -m gpu."""
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+import graph_evaluator_model as G
+import oracle_lib as O
+import pyref as R
+from witness_util import Domain, mont, pack_program, random_expr, unmont
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+FR, FQ = R.FR, R.FQ
+M = R.R_
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def W():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mira_b200 import witness
+    return witness
+
+
+def dev(b: bytes):
+    return torch.frombuffer(bytearray(b) if b else bytearray(1), dtype=torch.uint8).cuda()[: len(b)]
+
+
+def host(t) -> bytes:
+    return t.cpu().numpy().tobytes()
+
+
+def gpu_domain(W, d: Domain):
+    b = d.as_bytes()
+    return W.PlonkEvalDomain(d.num_advice, d.num_lookup, b["challenges"], [dev(s) for s in b["selectors"]],
+                             [dev(f) for f in b["fixed"]], [dev(w) for w in b["w1"]], [dev(w) for w in b["w2"]],
+                             row_size=d.row_size)
+
+
+def gpu_eval(W, field, ge: G.GraphEvaluator, gd):
+    p = pack_program(ge)
+    prog = W.GraphEvaluator(field, p["code"], p["constants"], p["rotations"], p["num_intermediates"])
+    out = host(prog.evaluate_rows(gd))
+    st = prog.stats()
+    prog.close()
+    return out, st
+
+
+def both(W, field, expr, d: Domain, gd=None):
+    ge = G.GraphEvaluator.new(expr, d.m)
+    want = O.eval_rows(field, pack_program(ge), d.as_bytes())
+    got, _ = gpu_eval(W, field, ge, gd or gpu_domain(W, d))
+    return got, want
+
+
+# ---- restatements of the reference's evaluator tests (graph_evaluator.rs:447-634), GPU vs oracle vs direct
+def test_constants_and_challenges(W):
+    d = Domain(M, 3, 0, 1, 0, 0, 1, 3, seed=3)
+    gd = gpu_domain(W, d)
+    rng = random.Random(1)
+    a, b = rng.randrange(M), rng.randrange(M)
+    for e, want in ((G.Constant(a), a), (G.Constant(a) + G.Constant(b), (a + b) % M), (G.Constant(a) * G.Constant(b), a * b % M),
+                    (-G.Constant(a), (-a) % M), (G.Challenge(2), d.challenges[2]), (G.Constant(0), 0)):
+        got, ora = both(W, FR, e, d, gd)
+        assert got == ora == mont([want] * 3, M)
+
+
+def test_poly_rotations_and_column_dispatch(W):
+    d = Domain(M, 2, 2, 2, 2, 0, 1, 0, seed=2)
+    gd = gpu_domain(W, d)
+    for base in (0, 2, 4, 6):         # selectors, fixed, advice of instance 1, advice of instance 2
+        for col in range(2):
+            for rot in (0, 1, -1, 2, -3):
+                e = G.Polynomial(base + col, rot)
+                got, ora = both(W, FR, e, d, gd)
+                assert got == ora == mont(d.direct(e, range(2)), M)
+
+
+def test_eval_example(W):
+    d = Domain(M, 2, 2, 2, 2, 0, 1, 0, seed=4)
+    adv = lambda c: G.Polynomial(4 + c)
+    zero = G.Constant(0)
+    e = (adv(0) + (adv(1) + (adv(1) + zero))) * (G.Polynomial(2) + (adv(0) + zero))
+    got, ora = both(W, FR, e, d)
+    assert got == ora == mont(d.direct(e, range(2)), M)
+
+
+def test_index_errors_match_the_reference(W):
+    d = Domain(M, 4, 0, 1, 2, 0, 1, 1, seed=5)
+    gd = gpu_domain(W, d)
+    for e, kind in ((G.Challenge(1), "ChallengeIndexOutOfBoundary"), (G.Polynomial(1 + 2 * 2), "InvalidWitnessIndex")):
+        ge = G.GraphEvaluator.new(e, M)
+        with pytest.raises(O.EvalError):
+            O.eval_rows(FR, pack_program(ge), d.as_bytes())
+        with pytest.raises(W.EvalError) as ex:
+            gpu_eval(W, FR, ge, gd)
+        assert ex.value.kind == kind
+    # a witness vector shorter than (j+1)*row_size is InvalidWitnessIndex too (src/plonk/eval.rs:206-214)
+    short = gpu_domain(W, d)
+    short.W1s = [short.W1s[0][: 32 * 7]]
+    with pytest.raises(W.EvalError) as ex:
+        gpu_eval(W, FR, G.GraphEvaluator.new(G.Polynomial(1 + 1), M), short)
+    assert ex.value.kind == "InvalidWitnessIndex"
+
+
+@pytest.mark.parametrize("field,m", [(FR, R.R_), (FQ, R.P)])
+@pytest.mark.parametrize("seed", range(4))
+def test_random_expressions(W, field, m, seed):
+    rng = random.Random(200 + seed)
+    n_sel, n_fix, n_adv, n_ch = 2, 3, 4, 3
+    rows = 37                                   # ragged: not a multiple of the block size
+    d = Domain(m, rows, n_sel, n_fix, n_adv, 0, 1, n_ch, seed=seed, sparse=(seed % 2 == 1))
+    gd = gpu_domain(W, d)
+    n_cols = n_sel + n_fix + 2 * n_adv
+    for _ in range(8):
+        e = random_expr(rng, m, n_cols, n_ch, depth=7, rotations=(0, 1, -1, 5))
+        got, ora = both(W, field, e, d, gd)
+        assert got == ora
+    e = random_expr(rng, m, n_cols, n_ch, depth=5)
+    assert both(W, field, e, d, gd)[0] == mont(d.direct(e, range(rows)), m)
+
+
+def test_lookup_column_mapping(W):
+    for n_w in (2, 3):
+        d = Domain(M, 4, 1, 1, 2, 2, n_w, 0, seed=20 + n_w)
+        gd = gpu_domain(W, d)
+        for idx in range(2 * (2 + 5 * 2)):
+            got, ora = both(W, FR, G.Polynomial(2 + idx), d, gd)
+            assert got == ora
+
+
+def test_horner_and_non_ssa_programs(W):
+    """Calculation::Horner is never emitted by add_expression but is part of the evaluator (graph_evaluator.rs:139-146)."""
+    d = Domain(M, 5, 0, 2, 2, 0, 1, 1, seed=9)
+    gd = gpu_domain(W, d)
+    K, I, P, CH = G.VS_CONSTANT, G.VS_INTERMEDIATE, G.VS_POLY, G.VS_CHALLENGE
+    ge = G.GraphEvaluator(M)
+    ge.constants += [12345, M - 7]
+    ge.rotations = [0, 1]
+    ge.calculations = [
+        ((G.OP_STORE, (P, 2, 0)), 0),
+        ((G.OP_STORE, (P, 3, 1)), 1),
+        ((G.OP_HORNER, (I, 0, 0), (CH, 0, 0), (I, 1, 0), (K, 3, 0), (P, 0, 0)), 2),   # start, factor, parts...
+        ((G.OP_HORNER, (I, 2, 0), (K, 4, 0)), 3),                                       # no parts: plain copy
+        ((G.OP_MUL, (I, 3, 0), (I, 5, 0)), 4),                                          # intermediate 5 never written: ZERO
+        ((G.OP_ADD, (I, 4, 0), (I, 2, 0)), 2),                                          # re-defines 2 (non-SSA)
+        ((G.OP_SQUARE, (I, 2, 0)), 6),
+    ]
+    ge.num_intermediates = 7
+    want = O.eval_rows(FR, pack_program(ge), d.as_bytes())
+    got, st = gpu_eval(W, FR, ge, gd)
+    assert got == want
+    # direct: h = ((a*c + b)*c + k)*c + f0 ; result = h^2
+    c = d.challenges[0]
+    exp = []
+    for r in range(5):
+        a, b, f0 = d.column(2, r), d.column(3, (r + 1) % 5), d.column(0, r)
+        h = (((a * c + b) * c + 12345) * c + f0) % M
+        exp.append(h * h % M)
+    assert got == mont(exp, M)
+
+
+@pytest.mark.parametrize("T,n_gates", [(5, 1), (5, 2)])
+def test_cross_term_programs_vs_oracle(W, T, n_gates):
+    progs, meta = G.cross_term_programs(T, n_gates, M)
+    rows = 1 << 11
+    d = Domain(M, rows, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=77 + n_gates, sparse=True)
+    gd = gpu_domain(W, d)
+    db = d.as_bytes()
+    for p in progs:
+        got, st = gpu_eval(W, FR, p, gd)
+        assert got == O.eval_rows(FR, pack_program(p), db)
+        assert st["muls"] == p.counts()["mul"] and st["slots"] <= 64
+
+
+def test_golden_eval_vectors(W):
+    with open(os.path.join(GOLDEN, "eval_vectors.json")) as f:
+        vecs = json.load(f)
+    cache = {}
+    for v in vecs:
+        key = (v["T"], v["n_gates"])
+        if key not in cache:
+            progs, meta = G.cross_term_programs(v["T"], v["n_gates"], M)
+            d = Domain(M, v["rows"], 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"],
+                       seed=v["domain_seed"], sparse=True)
+            cache[key] = (progs, gpu_domain(W, d))
+        progs, gd = cache[key]
+        got, _ = gpu_eval(W, FR, progs[v["term"] - 1], gd)
+        assert hashlib.sha256(got).hexdigest() == v["sha256"]
+
+
+def test_cross_terms_feed_commit_without_leaving_the_device(W):
+    """commit_cross_terms (src/nifs/vanilla/mod.rs:80-140): evaluate on the GPU, commit the device vector, and
+    compare with the oracle doing both steps on the CPU."""
+    from mira_b200 import BN254_G1, CommitmentKey
+    progs, meta = G.cross_term_programs(5, 1, M)
+    rows = 1 << 10
+    d = Domain(M, rows, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=123, sparse=True)
+    gd = gpu_domain(W, d)
+    bases = O.gen_bases(R.BN254, 0x4D495241, rows)
+    ck = CommitmentKey(BN254_G1, bases)
+    for p in progs[:3]:
+        pk = pack_program(p)
+        prog = W.GraphEvaluator(FR, pk["code"], pk["constants"], pk["rotations"], pk["num_intermediates"])
+        t_dev = prog.evaluate_rows(gd)
+        torch.cuda.synchronize()
+        got = ck.commit_device(t_dev.data_ptr(), rows)
+        want = O.commit(R.BN254, bases, O.eval_rows(FR, pk, d.as_bytes()))
+        assert got == want
+
+
+# ---- fold (src/plonk/mod.rs:1097-1134)
+@pytest.mark.parametrize("field,curve,m", [(FR, R.BN254, R.R_), (FQ, R.GRUMPKIN, R.P)])
+def test_fold_w_and_e(W, field, curve, m):
+    n = 100_003
+    w1 = O.gen_scalars(curve, 1, n, 1)
+    w2 = O.gen_scalars(curve, 2, n, 0)
+    r = O.gen_scalars(curve, 3, 1, 0)
+    d1, d2 = dev(w1), dev(w2)
+    assert host(W.fold_w(field, d1, d2, r)) == O.fold_w(field, w1, w2, r)
+    for n_terms in (0, 1, 5, 6):
+        ts = [O.gen_scalars(curve, 10 + k, n, k % 2) for k in range(n_terms)]
+        got = host(W.fold_e(field, d1, [dev(t) for t in ts], r))
+        assert got == O.fold_e(field, w1, ts, r)
+    W.fold_w(field, d1, d2, r, out=d1)          # in place, as a Rust `W = ...` replacing the accumulator would
+    assert host(d1) == O.fold_w(field, w1, w2, r)
+    edge = mont([0, 1, m - 1, m - 2, 2], m)
+    rm1 = R.to_mont_bytes(m - 1, m)
+    assert host(W.fold_w(field, dev(edge), dev(edge), rm1)) == O.fold_w(field, edge, edge, rm1) == bytes(160)
+    assert W.fold_w(field, dev(b""), dev(b""), r).numel() == 0
+
+
+def test_fold_is_what_is_sat_relaxed_checks(W):
+    """commit(W1 + r*W2) == commit(W1) + r*commit(W2): fold on the GPU, commit on the GPU, combine on the CPU
+    (src/plonk/mod.rs:547-557 via src/nifs/vanilla/tests.rs:137-244)."""
+    from mira_b200 import BN254_G1, CommitmentKey
+    n = 3000
+    bases = O.gen_bases(R.BN254, 5, n)
+    ck = CommitmentKey(BN254_G1, bases)
+    w1, w2 = O.gen_scalars(R.BN254, 6, n, 1), O.gen_scalars(R.BN254, 7, n, 1)
+    r = O.gen_scalars(R.BN254, 8, 1)
+    folded = W.fold_w(FR, dev(w1), dev(w2), r)
+    torch.cuda.synchronize()
+    lhs = ck.commit_device(folded.data_ptr(), n)
+    rhs = O.point_add(R.BN254, ck.commit(w1), O.scalar_mul(R.BN254, ck.commit(w2), r))
+    assert lhs == rhs
+
+
+# ---- concatenate_with_padding (src/util.rs:189-193)
+def test_concat_pad(W):
+    cols = [mont(c, M) for c in ([1, 2, 3], [], [4, 5, 6, 7, 8], [9])]
+    got = host(W.concatenate_with_padding([dev(c) for c in cols], 4))
+    assert got == O.concat_pad(cols, 4)
+    big = [O.gen_scalars(R.BN254, 40 + i, 1000 + i, 1) for i in range(7)]
+    assert host(W.concatenate_with_padding([dev(c) for c in big], 1024)) == O.concat_pad(big, 1024)
+
+
+# ---- FFT (src/fft.rs)
+def test_fft_reference_kat(W):
+    with open(os.path.join(GOLDEN, "fft_kat_fr.json")) as f:
+        g = json.load(f)
+    a = dev(mont(g["input"], M))
+    W.fft(FR, a, g["log_n"])
+    assert unmont(host(a), M) == [int(x) for x in g["output"]]
+    W.ifft(FR, a, g["log_n"])
+    assert unmont(host(a), M) == g["input"]
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 4, 5, 6, 7, 8, 10, 11, 13, 16])
+def test_fft_vs_oracle_and_roundtrip(W, k):
+    n = 1 << k
+    vals = O.gen_scalars(R.BN254, 900 + k, n, 0)
+    a = dev(vals)
+    W.fft(FR, a, k)
+    assert host(a) == O.fft(FR, vals, k)
+    W.ifft(FR, a, k)
+    assert host(a) == vals                      # fft_random_input_test (src/fft.rs:266-279)
+    w = O.fft_omega(FR, k, inverse=True)        # best_fft with a caller-supplied omega
+    b = dev(vals)
+    W.best_fft(FR, b, w, k)
+    assert host(b) == O.best_fft(FR, vals, k, w)
+
+
+def test_fft_large_roundtrip_and_linearity(W):
+    """2^22 elements: size-independent properties (round trip; FFT(a + c*b) = FFT(a) + c*FFT(b))."""
+    from gpu_util import gen_scalars_dev
+    k = 22
+    n = 1 << k
+    a = gen_scalars_dev(R.BN254, 1, n)
+    b = gen_scalars_dev(R.BN254, 2, n)
+    c = O.gen_scalars(R.BN254, 3, 1)
+    ab = W.fold_w(FR, a, b, c)
+    a0 = a.clone()
+    W.fft(FR, a, k); W.fft(FR, b, k); W.fft(FR, ab, k)
+    assert torch.equal(W.fold_w(FR, a, b, c), ab)
+    W.ifft(FR, a, k)
+    assert torch.equal(a, a0)
+
+
+def test_fft_size_limits(W):
+    a = dev(mont([1, 2], M))
+    with pytest.raises(ValueError):
+        W.fft(FQ, a, 1)                        # no ROOT_OF_UNITY path for Fq (S = 1)
+    with pytest.raises(ValueError):
+        W.fft(FR, a, 2)                        # assert_eq!(n, 1 << log_n)
