@@ -288,6 +288,107 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ fold-step replay
+def run_fold_step(args):
+    """`--workload fold-step`: BASELINE.json's second metric (IVC fold-step ms), as a replay of the hot-path work of one
+    SnarkStar fold step (tools/fold_step.py; the Rust driver itself cannot be built here).  Single GPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fold_step as F
+    hbm_peak, peak_src, sm_max = measured_peaks()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        cpu = F.CpuFoldStep(args.log_rows)
+        for _ in range(min(args.warmup, 1)):
+            cpu.step()
+        t0 = time.perf_counter()
+        steps = max(1, min(args.steps, 2))
+        for _ in range(steps):
+            cpu.step()
+        ms = (time.perf_counter() - t0) / steps * 1e3
+        import oracle_lib as O
+        out = {"impl": "reference", "metric": "IVC fold-step hot-path ms", "value": round(ms, 1), "unit": "ms", "n_gpus": 1,
+               "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 1), "higher_is_better": False,
+               "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (254-bit Montgomery, integer)", "data": "synthetic",
+               "config": {"workload": f"SnarkStar fold-step replay, k={args.log_rows}: witness commits + cross-term evaluation + "
+                                      f"cross-term commits + fold, both circuits", "points_per_step": F.points_per_step(cpu.sh)},
+               "cpu_baseline": {"value": round(ms, 1), "unit": "ms", "cores": O.num_cores(), "kind": "port",
+                                "sample": "one full step on the host CPU through oracle/ (C restatement; the Rust reference cannot be built here)"},
+               "e2e": {"value": round(ms, 1), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — mira_b200 has no CPU fallback")
+    g = F.GpuFoldStep(args.log_rows)
+
+    def timed(from_host, steps, warmup):
+        for _ in range(warmup):
+            res = g.step(from_host)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(g.stream)
+        for _ in range(steps):
+            res = g.step(from_host)
+        e1.record(g.stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, res
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_dev, res_dev = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e, res_e2e = timed(True, args.steps, 1)
+    assert res_dev == res_e2e
+    # phase split with CUDA events (one extra step): evaluation kernels alone
+    sh, st = g.sh, g.state
+    ev_ms, muls = 0.0, 0
+    from mira_b200 import witness as W
+    for s, t in zip(sh, st):
+        dom = W.PlonkEvalDomain(s["meta"]["num_advice"], 0, t["ch"], [], t["fixed"], [t["W1"]], [t["W2"]])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(g.stream)
+        for prog, tt in zip(t["progs"], t["T"]):
+            prog.evaluate_rows(dom, out=tt, stream=g.stream.cuda_stream)
+        e1.record(g.stream)
+        torch.cuda.synchronize()
+        ev_ms += e0.elapsed_time(e1)
+        muls += s["muls_per_row"] * s["rows"]
+    imad_peak = 148 * IMAD_WIDE_PER_CLK_PER_SM * sm_max * 1e6
+    pts = F.points_per_step(sh)
+    h2d = sum(s["n_w"] * 32 for s in sh)
+    ncommit = sum(1 + len(s["progs"]) for s in sh)
+    launches = sum(int(t["ck"].stats()["kernel_launches"]) for t in st)   # last commit of each key; lower bound per commit
+    out = {"metric": "IVC fold-step hot-path ms", "value": round(ms_dev, 3), "unit": "ms", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(ms_dev, 3), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u32x8 (254-bit Montgomery, integer)", "data": "synthetic",
+           "config": {"workload": f"SnarkStar fold-step replay, k={args.log_rows}: witness commits + cross-term evaluation + "
+                                  f"cross-term commits + fold, both circuits", "points_per_step": pts, "commits_per_step": ncommit,
+                      "l2": "working set (keys' fixed-base tables, W, fixed columns) is >> 126 MB L2; no flush needed",
+                      "seed": F.SEED},
+           "clocks": clocks,
+           "e2e": {"value": round(ms_e2e, 3), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64 * ncommit},
+           "gpu_launches": (ncommit * launches // max(len(st), 1) + g.launches_per_step()) * args.steps,
+           "phases_ms": {"cross_term_evaluation": round(ev_ms, 3), "commits_and_fold": round(ms_dev - ev_ms, 3)},
+           "roofline": {"kernel": "k_eval_rows (all 11 cross-term programs)", "bound": "hbm", "achieved": None, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                        "note": "integer-pipe bound kernel, see roofline_imad; the MSM kernels' roofline is in the default workload's line"},
+           "roofline_imad": {"kernel": "k_eval_rows", "bound": "imad.wide.u32", "achieved": round(muls * MACS_PER_MODMUL / (ev_ms * 1e-3) / 1e12, 3),
+                             "peak": round(imad_peak / 1e12, 3), "unit": "T wide-MAC/s",
+                             "frac": round(muls * MACS_PER_MODMUL / (ev_ms * 1e-3) / imad_peak, 4)}}
+    if not args.no_cpu_baseline:
+        import oracle_lib as O
+        cpu = F.CpuFoldStep(args.log_rows, inputs=g.host_inputs())
+        t0 = time.perf_counter()
+        want = cpu.step()
+        dt = (time.perf_counter() - t0) * 1e3
+        assert want == res_dev, "GPU fold-step commitments differ from the CPU oracle's"
+        out["cpu_baseline"] = {"value": round(dt, 1), "unit": "ms", "cores": O.num_cores(), "kind": "port",
+                               "sample": "one full step of the same workload (same bytes) through oracle/; commitments compared bit for bit"}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -298,7 +399,12 @@ def main():
     ap.add_argument("--curve", default="bn254", choices=["bn254", "grumpkin"])
     ap.add_argument("--cpu-sample-log-n", type=int, default=21, help="log2(points) of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="msm", choices=["msm", "fold-step"],
+                    help="msm: the headline BN254 MSM (default); fold-step: replay of one SnarkStar IVC fold step")
+    ap.add_argument("--log-rows", type=int, default=19, help="fold-step: log2(rows) of the circuit tables (k)")
     args = ap.parse_args()
+    if args.workload == "fold-step":
+        return run_fold_step(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU (the driver uses torchrun directly)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

@@ -16,29 +16,41 @@
 
 namespace mira_host {
 
-constexpr int RS_THREADS = 512;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                       // pairs per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // 8192 pairs per tile
 constexpr int RS_BINS = 256;
-constexpr int RS_WARP_TILE = 32 * RS_ITEMS;        // 512 consecutive pairs per warp
+constexpr int RS_ITEMS = 16;                       // pairs per thread
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
-                                                           int shift, uint32_t* __restrict__ hist, uint32_t n_tiles) {
+// Tile geometry: THREADS x RS_ITEMS pairs per tile.  <256>: 4096-pair tiles, ~42 KB of shared memory and <= 80
+// registers, so three to four blocks are resident per SM (the 512-thread / 8192-pair variant fitted one).
+template <int THREADS> struct RsCfg {
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int TILE = THREADS * RS_ITEMS;
+  static constexpr int WARP_TILE = 32 * RS_ITEMS;  // consecutive pairs owned by one warp
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_radix_hist(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
+                                                        int shift, uint32_t* __restrict__ hist, uint32_t n_tiles) {
+  constexpr int TILE = RsCfg<THREADS>::TILE;
   __shared__ uint32_t sh[RS_BINS];
   const uint32_t n = *n_ptr;
-  const uint32_t base = blockIdx.x * RS_TILE;
-  if (threadIdx.x < RS_BINS) sh[threadIdx.x] = 0;
+  const uint32_t base = blockIdx.x * TILE;
+  for (int i = threadIdx.x; i < RS_BINS; i += THREADS) sh[i] = 0;
   __syncthreads();
   if (base < n) {
+    uint32_t kk[RS_ITEMS];                       // all loads in flight before the first shared-memory atomic
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; k++) {
-      uint32_t idx = base + k * RS_THREADS + threadIdx.x;
-      if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & 0xffu], 1u);
+      uint32_t idx = base + k * THREADS + threadIdx.x;
+      kk[k] = idx < n ? __ldg(keys + idx) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+      uint32_t idx = base + k * THREADS + threadIdx.x;
+      if (idx < n) atomicAdd(&sh[(kk[k] >> shift) & 0xffu], 1u);
     }
   }
   __syncthreads();
-  if (threadIdx.x < RS_BINS) hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
+  for (int i = threadIdx.x; i < RS_BINS; i += THREADS) hist[(size_t)i * n_tiles + blockIdx.x] = sh[i];
 }
 
 // ---- exclusive scan over the [256 * n_tiles] histogram (3 phases, same scheme as the bucket offsets)
@@ -114,44 +126,71 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_down(uint32_t* __restrict__
 }
 
 // ---- stable scatter of one tile
+template <int THREADS>
 struct RsSmem {
-  uint32_t cnt[RS_WARPS][RS_BINS + 1];   // per-warp digit counts -> per-warp exclusive offsets (bin 256 = padding)
-  uint32_t dstart[RS_BINS + 1];          // first tile-local slot of each digit
-  uint32_t gbase[RS_BINS];               // global base of (digit, this tile)
+  uint32_t cnt[RsCfg<THREADS>::WARPS][RS_BINS + 1];   // per-warp digit counts -> per-warp exclusive offsets (bin 256 = padding)
+  uint32_t dstart[RS_BINS + 1];                       // first tile-local slot of each digit
+  uint32_t gbase[RS_BINS];                            // global base of (digit, this tile)
   uint32_t scan_tmp[32];
-  uint32_t keys[RS_TILE];
-  uint32_t vals[RS_TILE];
+  uint32_t keys[RsCfg<THREADS>::TILE];
+  uint32_t vals[RsCfg<THREADS>::TILE];
+  uint32_t vals_in[RsCfg<THREADS>::TILE];             // the tile's values, staged with cp.async while keys are ranked
 };
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                              const uint32_t* __restrict__ n_ptr, int shift,
-                                                              const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles,
-                                                              uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                           const uint32_t* __restrict__ n_ptr, int shift,
+                                                           const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles,
+                                                           uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
+  using Cfg = RsCfg<THREADS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RsSmem& S = *reinterpret_cast<RsSmem*>(smem_raw);
+  RsSmem<THREADS>& S = *reinterpret_cast<RsSmem<THREADS>*>(smem_raw);
   const uint32_t n = *n_ptr;
-  const uint32_t tile_base = blockIdx.x * RS_TILE;
+  const uint32_t tile_base = blockIdx.x * Cfg::TILE;
   if (tile_base >= n) return;
-  const uint32_t tile_count = (n - tile_base) < (uint32_t)RS_TILE ? (n - tile_base) : (uint32_t)RS_TILE;
+  const uint32_t tile_count = (n - tile_base) < (uint32_t)Cfg::TILE ? (n - tile_base) : (uint32_t)Cfg::TILE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  for (int i = threadIdx.x; i < RS_WARPS * (RS_BINS + 1); i += RS_THREADS) (&S.cnt[0][0])[i] = 0;
-  if (threadIdx.x < RS_BINS) S.gbase[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * n_tiles + blockIdx.x];
+  for (int i = threadIdx.x; i < Cfg::WARPS * (RS_BINS + 1); i += THREADS) (&S.cnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < RS_BINS; i += THREADS) S.gbase[i] = hist_scanned[(size_t)i * n_tiles + blockIdx.x];
   __syncthreads();
 
-  // phase 1: warp-private stable ranks.  Warp w owns the 512 consecutive pairs starting at w*512.
-  uint32_t k[RS_ITEMS], v[RS_ITEMS];
+  // phase 0: every load of the tile is issued up front (the kernel is latency-bound otherwise): keys into
+  // registers, values through cp.async into shared memory where phase 3 picks them up.
+  uint32_t k[RS_ITEMS];
   uint16_t rank[RS_ITEMS];
   uint32_t* my_cnt = S.cnt[warp];
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; r++) {
-    uint32_t local = warp * RS_WARP_TILE + r * 32 + lane;
+    uint32_t local = warp * Cfg::WARP_TILE + r * 32 + lane;
+    k[r] = local < tile_count ? __ldg(keys + tile_base + local) : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    uint32_t local = warp * Cfg::WARP_TILE + r * 32 + lane;
+    if (local < tile_count) {
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.vals_in[local]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(vals + tile_base + local) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // phase 1: warp-private stable ranks.  Warp w owns the WARP_TILE consecutive pairs starting at w*WARP_TILE.
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    uint32_t local = warp * Cfg::WARP_TILE + r * 32 + lane;
     bool valid = local < tile_count;
-    k[r] = valid ? keys[tile_base + local] : 0u;
-    v[r] = valid ? vals[tile_base + local] : 0u;
     uint32_t d = valid ? ((k[r] >> shift) & 0xffu) : (uint32_t)RS_BINS;
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    // lanes holding the same digit: one ballot per digit bit (cost independent of how many distinct digits the
+    // warp holds, unlike MATCH.ANY); invalid lanes (ragged last tile) form their own group on bin 256
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+    if (!valid) peers = ~peers;
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+      uint32_t b = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
+      peers &= ((d >> bit) & 1u) ? b : ~b;
+    }
     int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (lane == leader) {
@@ -169,7 +208,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __
   if (threadIdx.x < RS_BINS) {
     uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) {
+    for (int w = 0; w < Cfg::WARPS; w++) {
       uint32_t t = S.cnt[w][threadIdx.x];
       S.cnt[w][threadIdx.x] = run;
       run += t;
@@ -179,24 +218,25 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __
   uint32_t tile_total;
   uint32_t ds = block_excl_scan(total, S.scan_tmp, tile_total);
   if (threadIdx.x < RS_BINS) S.dstart[threadIdx.x] = ds;
-  if (threadIdx.x == RS_BINS) S.dstart[RS_BINS] = tile_total;
+  if (threadIdx.x == 0) S.dstart[RS_BINS] = tile_total;
   __syncthreads();
 
-  // phase 3: place every pair at its tile-local sorted slot
+  // phase 3: place every pair at its tile-local sorted slot (each thread reads back the values it staged itself)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; r++) {
-    uint32_t local = warp * RS_WARP_TILE + r * 32 + lane;
+    uint32_t local = warp * Cfg::WARP_TILE + r * 32 + lane;
     if (local < tile_count) {
       uint32_t d = (k[r] >> shift) & 0xffu;
       uint32_t q = S.dstart[d] + my_cnt[d] + rank[r];
       S.keys[q] = k[r];
-      S.vals[q] = v[r];
+      S.vals[q] = S.vals_in[local];
     }
   }
   __syncthreads();
 
   // phase 4: stream the re-ordered tile out; a digit's run is contiguous in both smem and HBM
-  for (uint32_t q = threadIdx.x; q < tile_count; q += RS_THREADS) {
+  for (uint32_t q = threadIdx.x; q < tile_count; q += THREADS) {
     uint32_t key = S.keys[q];
     uint32_t d = (key >> shift) & 0xffu;
     uint32_t dst = S.gbase[d] + (q - S.dstart[d]);
@@ -204,6 +244,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __
     out_vals[dst] = S.vals[q];
   }
 }
+
+constexpr int RS_THREADS = 256;                    // the shipped geometry
+constexpr int RS_TILE = RsCfg<RS_THREADS>::TILE;
 
 size_t radix_sort_temp_bytes(size_t max_pairs) {
   size_t n_tiles = (max_pairs + RS_TILE - 1) / RS_TILE;
@@ -220,7 +263,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   int dev = 0;
   CU(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    CU(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+    CU(cudaFuncSetAttribute(k_radix_scatter<RS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<RS_THREADS>)));
     attr_set[dev] = true;
   }
   const uint32_t n_tiles = (uint32_t)((max_pairs + RS_TILE - 1) / RS_TILE);
@@ -237,11 +280,11 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   uint32_t *ka = keys_a, *va = vals_a, *kb = keys_b, *vb = vals_b;
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
-    k_radix_hist<<<n_tiles, RS_THREADS, 0, st>>>(ka, n_ptr, shift, hist, n_tiles);
+    k_radix_hist<RS_THREADS><<<n_tiles, RS_THREADS, 0, st>>>(ka, n_ptr, shift, hist, n_tiles);
     k_scan_sums<<<n_sums, SC_THREADS, 0, st>>>(hist, hist_n, sums);
     k_scan_top<<<1, SC_THREADS, 0, st>>>(sums, n_sums);
     k_scan_down<<<n_sums, SC_THREADS, 0, st>>>(hist, hist_n, sums);
-    k_radix_scatter<<<n_tiles, RS_THREADS, sizeof(RsSmem), st>>>(ka, va, n_ptr, shift, hist, n_tiles, kb, vb);
+    k_radix_scatter<RS_THREADS><<<n_tiles, RS_THREADS, sizeof(RsSmem<RS_THREADS>), st>>>(ka, va, n_ptr, shift, hist, n_tiles, kb, vb);
     if (launches) *launches += 5;
     std::swap(ka, kb);
     std::swap(va, vb);

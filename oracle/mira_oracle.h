@@ -112,6 +112,14 @@ int oracle_eval_rows(int field, const uint32_t *code, size_t code_words, const v
                      const int32_t *rotations, size_t n_rotations, uint32_t num_intermediates,
                      const oracle_eval_domain *dom, size_t row_begin, size_t row_end, void *out);
 
+/* the same three loops split over `threads` pthreads (<= 0: all cores), as the reference runs them under rayon */
+int oracle_eval_rows_mt(int field, const uint32_t *code, size_t code_words, const void *constants, size_t n_constants,
+                        const int32_t *rotations, size_t n_rotations, uint32_t num_intermediates,
+                        const oracle_eval_domain *dom, int threads, void *out);
+void oracle_fold_w_mt(int field, const void *w1, const void *w2, size_t n, const void *r, int threads, void *out);
+void oracle_fold_e_mt(int field, const void *e, const void *const *terms, size_t n_terms, size_t n, const void *r,
+                      int threads, void *out);
+
 /* fft::best_fft (src/fft.rs:51-115) in place over 2^log_n elements, and its helpers / wrappers */
 void oracle_fft(int field, void *a, uint32_t log_n, const void *omega);
 int  oracle_fft_omega(int field, uint32_t k, int is_inverse, void *out);   /* get_omega_or_inv; -1 if k > S */

@@ -329,3 +329,70 @@ int oracle_fft_inverse(int field, void *a_, uint32_t log_n) {
     for (size_t i = 0; i < ((size_t)1 << log_n); i++) fe_mul(f, &a[i], &a[i], &d);
     return 0;
 }
+
+/* ------------------------------------------------------------------ multi-threaded wrappers
+ * The reference runs these loops under rayon (`into_par_iter` over rows, src/nifs/vanilla/mod.rs:109-116;
+ * `par_iter` in fold, src/plonk/mod.rs:1104-1131).  Used by bench.py's CPU baseline so the host cores are all busy. */
+typedef struct {
+    int kind, field, rc;
+    const uint32_t *code; size_t code_words; const void *constants; size_t n_constants;
+    const int32_t *rotations; size_t n_rotations; uint32_t num_intermediates; const oracle_eval_domain *dom;
+    const void *a, *b, *r; const void *const *terms; size_t n_terms;
+    size_t begin, end; void *out;
+} wjob;
+static void *wjob_run(void *p) {
+    wjob *j = p;
+    if (j->kind == 0)
+        j->rc = oracle_eval_rows(j->field, j->code, j->code_words, j->constants, j->n_constants, j->rotations, j->n_rotations,
+                                 j->num_intermediates, j->dom, j->begin, j->end, (char *)j->out + j->begin * 32);
+    else if (j->kind == 1)
+        oracle_fold_w(j->field, (const char *)j->a + j->begin * 32, (const char *)j->b + j->begin * 32, j->end - j->begin, j->r,
+                      (char *)j->out + j->begin * 32);
+    else {
+        const void *shifted[64];
+        for (size_t k = 0; k < j->n_terms; k++) shifted[k] = (const char *)j->terms[k] + j->begin * 32;
+        oracle_fold_e(j->field, (const char *)j->a + j->begin * 32, shifted, j->n_terms, j->end - j->begin, j->r,
+                      (char *)j->out + j->begin * 32);
+    }
+    return NULL;
+}
+static int run_jobs(wjob proto, size_t n, int threads) {
+    if (threads <= 0) threads = oracle_num_cores();
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    pthread_t *th = malloc(sizeof(pthread_t) * threads);
+    wjob *jobs = malloc(sizeof(wjob) * threads);
+    size_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = proto;
+        jobs[t].begin = (size_t)t * per < n ? (size_t)t * per : n;
+        jobs[t].end = jobs[t].begin + per < n ? jobs[t].begin + per : n;
+        pthread_create(&th[t], NULL, wjob_run, &jobs[t]);
+    }
+    int rc = 0;
+    for (int t = 0; t < threads; t++) {
+        pthread_join(th[t], NULL);
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    free(th);
+    free(jobs);
+    return rc;
+}
+int oracle_eval_rows_mt(int field, const uint32_t *code, size_t code_words, const void *constants, size_t n_constants,
+                        const int32_t *rotations, size_t n_rotations, uint32_t num_intermediates,
+                        const oracle_eval_domain *dom, int threads, void *out) {
+    wjob j = {0};
+    j.kind = 0; j.field = field; j.code = code; j.code_words = code_words; j.constants = constants; j.n_constants = n_constants;
+    j.rotations = rotations; j.n_rotations = n_rotations; j.num_intermediates = num_intermediates; j.dom = dom; j.out = out;
+    return run_jobs(j, dom->row_size, threads);
+}
+void oracle_fold_w_mt(int field, const void *w1, const void *w2, size_t n, const void *r, int threads, void *out) {
+    wjob j = {0};
+    j.kind = 1; j.field = field; j.a = w1; j.b = w2; j.r = r; j.out = out;
+    run_jobs(j, n, threads);
+}
+void oracle_fold_e_mt(int field, const void *e, const void *const *terms, size_t n_terms, size_t n, const void *r, int threads,
+                      void *out) {
+    wjob j = {0};
+    j.kind = 2; j.field = field; j.a = e; j.terms = terms; j.n_terms = n_terms; j.r = r; j.out = out;
+    run_jobs(j, n, threads);
+}
