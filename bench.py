@@ -35,6 +35,7 @@ SEED_SCALARS = 0x4D495242
 IMAD_WIDE_PER_CLK_PER_SM = 32    # measured, profiles/r01_intpipe_microbench.jsonl
 MACS_PER_MODMUL = 136            # 8-limb CIOS: 2*8^2 + 8
 MODMUL_PER_MADD = 10             # XYZZ mixed add 8M + 2S
+ACC_DRAM_BYTES_PER_PAIR = 29.09e9 / 201326592   # measured, profiles/r01_accumulate_v3.txt
 
 
 def measured_peaks():
@@ -116,6 +117,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     curve = curve_id(args.curve)
     n = 1 << args.log_n                      # points per rank
@@ -225,7 +227,10 @@ def run_ours(args):
         "phases_ms": {k: round(v, 3) for k, v in prof.items()},
         "roofline": {"kernel": "k_accumulate (+k_combine)", "bound": "hbm", "achieved": round(alg_bytes / acc_s / 1e9, 1),
                      "peak": hbm_peak, "unit": "GB/s", "frac": round(alg_bytes / acc_s / 1e9 / hbm_peak, 4),
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": round(entries * ACC_DRAM_BYTES_PER_PAIR / 1e9, 2), "traffic_unit": "GB per launch",
+                     "traffic_source": "ncu --set full, profiles/r01_accumulate_v3.txt: 29.09 GB dram read+write for 201.3 M pairs "
+                                       "(each 64 B gathered point costs a 128 B DRAM burst), scaled to this launch's pairs",
+                     "peak_source": peak_src,
                      "note": "kernel is integer-pipe bound, see roofline_imad"},
         "roofline_imad": {"kernel": "k_accumulate (+k_combine)", "bound": "imad.wide.u32", "achieved": round(macs / acc_s / 1e12, 3),
                           "peak": round(imad_peak / 1e12, 3), "unit": "T wide-MAC/s", "frac": round(macs / acc_s / imad_peak, 4),

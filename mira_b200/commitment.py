@@ -189,6 +189,10 @@ class CommitmentKey:
     def set_window(self, c: int):
         _check(N.lib().mira_msm_set_window(self._ctx, c))
 
+    def set_slice_min(self, n: int):
+        """Host-buffer commits are pipelined in up to 4 slices of >= n scalars behind their H2D copies (0: off)."""
+        _check(N.lib().mira_msm_set_slice_min(self._ctx, n))
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             N.lib().mira_msm_ctx_destroy(self._ctx)

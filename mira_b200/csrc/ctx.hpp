@@ -61,11 +61,15 @@ struct mira_msm_ctx {
   size_t n_bases = 0;
   void* d_bases = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;          // H2D of host-buffer commits, overlapped with compute slice by slice
+  cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t compute_idle = nullptr;
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
   void* h_result = nullptr;  // pinned, 256 B
   int forced_window = 0;
+  size_t slice_min = (size_t)1 << 21;          // host-buffer commits are pipelined in up to 4 slices of >= this many scalars
   bool profiling = false;
   mira_msm_stats stats{};
   std::mutex mu;

@@ -99,6 +99,10 @@ void mira_msm_ctx_destroy(mira_msm_ctx* ctx) {
     b->release();
   if (ctx->d_bases) cudaFree(ctx->d_bases);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  for (auto& e : ctx->copy_done)
+    if (e) cudaEventDestroy(e);
+  if (ctx->compute_idle) cudaEventDestroy(ctx->compute_idle);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -152,6 +156,12 @@ int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
   if (window_bits != 0 && (window_bits < 2 || window_bits > 26)) return fail(MIRA_ERR_INVALID, "window must be 0 or in [2, 26]");
   ctx->forced_window = window_bits;
+  return MIRA_OK;
+}
+
+int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
+  if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  ctx->slice_min = min_scalars_per_slice ? min_scalars_per_slice : ~(size_t)0;   // 0 = never slice
   return MIRA_OK;
 }
 

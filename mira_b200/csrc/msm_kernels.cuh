@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t signed_digit(const uint32_t (&s)[8], int j, 
 }
 
 template <class SF>
-__global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ scalars, uint32_t n, int c, int W,
+__global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ scalars, uint32_t n, uint32_t first, int c, int W,
                                                        uint32_t n_cover, uint32_t* __restrict__ keys,
                                                        uint32_t* __restrict__ refs, uint32_t* __restrict__ n_out) {
   extern __shared__ uint32_t sm_cnt[];       // [W][DG_WARPS] pair counts -> offsets, then [0] = block base
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ 
     if (d) {
       uint32_t pos = base + sm_cnt[j * DG_WARPS + warp] + __popc(b & lt);
       keys[pos] = d;
-      refs[pos] = ((uint32_t)j * n_cover + i) | neg;
+      refs[pos] = ((uint32_t)j * n_cover + first + i) | neg;     // `scalars` is the slice starting at key index `first`
     }
   }
 }
@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
                                                     const uint32_t* __restrict__ srefs,
                                                     const uint32_t* __restrict__ n_ptr, int L,
                                                     const void* __restrict__ table, void* __restrict__ buckets,
-                                                    uint32_t* __restrict__ part_keys, void* __restrict__ part_pts) {
+                                                    uint32_t* __restrict__ part_keys, void* __restrict__ part_pts, int add_mode) {
+  // add_mode: the buckets already hold the sums of earlier scalar slices (host-buffer commits are pipelined slice
+  // by slice behind their H2D copies); the piece that owns a run's left end then starts from the bucket's value
+  // instead of the identity, so folding a slice in costs one 128-byte load per run and no extra group operation.
   const uint32_t n_sorted = *n_ptr;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   size_t begin = (size_t)t * L;
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
   bool first = true;
   uint32_t pk0 = 0, pk1 = 0;
   Xyzz<CF> acc = xyzz_identity<CF>();
+  if (add_mode && prev_key != cur) acc = xyzz_load_shared<CF>(reinterpret_cast<const char*>(buckets) + (size_t)cur * 128);
   for (size_t e = begin; e < end; e++) {
     uint32_t k = skeys[e];
     if (k != cur) {
@@ -140,7 +144,8 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
       }
       first = false;
       cur = k;
-      acc = xyzz_identity<CF>();
+      if (add_mode) acc = xyzz_load_shared<CF>(reinterpret_cast<const char*>(buckets) + (size_t)cur * 128);
+      else acc = xyzz_identity<CF>();
     }
     Affine<CF> p = load_ref<CF>(table, srefs[e]);
     xyzz_madd(acc, p);

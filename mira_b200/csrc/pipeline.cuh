@@ -80,50 +80,64 @@ struct PhaseTimer {
   }
 };
 
-// Runs the device pipeline; leaves the XYZZ sum (128 B) in ctx->result.p
-template <class CF, class SF>
-int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t st) {
+// The device pipeline is split so that a host-buffer commit can run it slice by slice behind the H2D copies:
+//   msm_begin   picks the window, fetches the fixed-base table, sizes the workspace, clears the buckets
+//   msm_slice   digits -> sort -> accumulate for scalars [first, first + n_slice); add_mode folds into the buckets
+//   msm_finish  bucket reduction; leaves the XYZZ sum (128 B) in ctx->result.p
+struct MsmPlan {
+  int c = 0, W = 0;
+  Table* tab = nullptr;
+  uint32_t B = 0;
+  size_t max_slice = 0;
   uint64_t launches = 0;
+  uint64_t entries = 0;
+};
+
+template <class CF>
+int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan) {
   int rc;
-  if ((rc = ctx->result.ensure(256))) return rc;
-  if (n == 0) {
-    CU(cudaMemsetAsync(ctx->result.p, 0, 128, st));
-    ctx->stats = mira_msm_stats{};
-    return MIRA_OK;
-  }
   int c = ctx->forced_window ? ctx->forced_window : choose_window(n);
   Table* tab = nullptr;
   if ((rc = get_table<CF>(ctx, c, n, &tab))) return rc;
   const int W = tab->W;
-  const size_t E = n * (size_t)W;
-  if (E >= (size_t)0x7fffffff || (size_t)W * tab->n_cover >= (size_t)0x7fffffff)
-    return fail(MIRA_ERR_INVALID, "commit of %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it", n, E);
+  const size_t E = max_slice * (size_t)W;
+  if (n * (size_t)W >= (size_t)0x7fffffff || (size_t)W * tab->n_cover >= (size_t)0x7fffffff)
+    return fail(MIRA_ERR_INVALID, "commit of %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it", n, n * (size_t)W);
   const uint32_t B = 1u << (c - 1);
-
   if ((rc = ctx->keys.ensure(E * 4 + 16)) || (rc = ctx->refs.ensure(E * 4 + 16)) || (rc = ctx->skeys.ensure(E * 4 + 16)) ||
       (rc = ctx->srefs.ensure(E * 4 + 16)) || (rc = ctx->counts.ensure(64)) || (rc = ctx->buckets.ensure(((size_t)B + 1) * 128)) ||
       (rc = ctx->tile_sums.ensure(radix_sort_temp_bytes(E))))
     return rc;
-  uint32_t* d_npairs = (uint32_t*)ctx->counts.p;     // number of (bucket, ref) pairs, produced on the device
+  CU(cudaMemsetAsync(ctx->buckets.p, 0, ((size_t)B + 1) * 128, st));
+  plan->c = c; plan->W = W; plan->tab = tab; plan->B = B; plan->max_slice = max_slice;
+  plan->launches = 0; plan->entries = 0;
+  return MIRA_OK;
+}
 
-  PhaseTimer pt(ctx->profiling, st);
-  pt.mark(0);
+template <class CF, class SF>
+int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, size_t first, size_t n, bool add_mode, cudaStream_t st,
+              PhaseTimer* pt) {
+  int rc;
+  const int c = plan->c, W = plan->W;
+  Table* tab = plan->tab;
+  const size_t E = n * (size_t)W;
+  uint32_t* d_npairs = (uint32_t*)ctx->counts.p;     // number of (bucket, ref) pairs, produced on the device
+  if (pt) pt->mark(0);
   // ---- digits (compacted pair list)
   CU(cudaMemsetAsync(d_npairs, 0, 4, st));
   k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
-      d_scalars, (uint32_t)n, c, W, tab->n_cover, (uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, d_npairs);
-  launches++;
-  pt.mark(1);
+      d_scalars, (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, d_npairs);
+  plan->launches++;
+  if (pt) pt->mark(1);
   // ---- group pairs by bucket: LSD radix sort on the c-bit key
   int in_b = 0;
   if ((rc = radix_sort_pairs((uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p, d_npairs, E, c,
-                             ctx->tile_sums.p, st, &in_b, &launches)))
+                             ctx->tile_sums.p, st, &in_b, &plan->launches)))
     return rc;
   const uint32_t* skeys = (const uint32_t*)(in_b ? ctx->skeys.p : ctx->keys.p);
   const uint32_t* srefs = (const uint32_t*)(in_b ? ctx->srefs.p : ctx->refs.p);
-  pt.mark(2);
+  if (pt) pt->mark(2);
   // ---- accumulate
-  CU(cudaMemsetAsync(ctx->buckets.p, 0, ((size_t)B + 1) * 128, st));
   {
     // Entries per thread: as long as possible (each chunk edge that falls inside a bucket's run costs one
     // XYZZ full add in k_combine) while keeping >= ~4 waves of 148 SMs x 512 resident threads.  Sized from
@@ -133,7 +147,7 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
     uint32_t n_chunks = (uint32_t)((E + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
     k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(skeys, srefs, d_npairs, L, tab->d, ctx->buckets.p,
-                                                            (uint32_t*)ctx->part_keys.p, ctx->part_pts.p);
+                                                            (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
     uint32_t heavy_cap = n_chunks / HEAVY_CHUNKS + 2;
     if ((rc = ctx->cursor.ensure(((size_t)heavy_cap + 2) * 4))) return rc;
     uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0] = count, [1..] = leader slots of heavy runs
@@ -142,15 +156,22 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
                                                              ctx->buckets.p, d_heavy, heavy_cap);
     k_combine_heavy<CF><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
                                                        ctx->buckets.p, d_heavy, heavy_cap);
-    launches += 3;
+    plan->launches += 3;
   }
-  pt.mark(3);
-  // ---- bucket reduction
+  if (pt) pt->mark(3);
+  plan->entries += E;
+  return MIRA_OK;
+}
+
+template <class CF>
+int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt) {
+  int rc;
+  const uint32_t B = plan->B;
   const uint32_t m = B >= (1u << 14) ? 32 : (B >= 1024 ? 8 : 1);
   uint32_t n_red = (B + m - 1) / m;
   if ((rc = ctx->red_a.ensure((size_t)n_red * 128)) || (rc = ctx->red_b.ensure((size_t)(n_red / 128 + 2) * 128))) return rc;
   k_reduce_chunks<CF><<<(n_red + 127) / 128, 128, 0, st>>>(ctx->buckets.p, B, m, ctx->red_a.p);
-  launches++;
+  plan->launches++;
   void* src = ctx->red_a.p;
   void* dst = ctx->red_b.p;
   uint32_t cnt = n_red;
@@ -159,18 +180,36 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
     uint32_t per_block = per_thread * 128;
     uint32_t blocks = (cnt + per_block - 1) / per_block;
     k_sum_points<CF><<<blocks, 128, 0, st>>>(src, cnt, per_thread, dst);
-    launches++;
+    plan->launches++;
     cnt = blocks;
     std::swap(src, dst);
   }
   CU(cudaMemcpyAsync(ctx->result.p, src, 128, cudaMemcpyDeviceToDevice, st));
-  pt.mark(4);
+  if (pt) pt->mark(4);
   CU(cudaGetLastError());
-  ctx->stats.window_bits = c;
-  ctx->stats.windows = W;
-  ctx->stats.entries = E;
+  ctx->stats.window_bits = plan->c;
+  ctx->stats.windows = plan->W;
+  ctx->stats.entries = plan->entries;
   ctx->stats.buckets = B;
-  ctx->stats.kernel_launches = launches;
+  ctx->stats.kernel_launches = plan->launches;
+  return MIRA_OK;
+}
+
+// Scalars resident in HBM: one slice.
+template <class CF, class SF>
+int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t st) {
+  int rc;
+  if ((rc = ctx->result.ensure(256))) return rc;
+  if (n == 0) {
+    CU(cudaMemsetAsync(ctx->result.p, 0, 128, st));
+    ctx->stats = mira_msm_stats{};
+    return MIRA_OK;
+  }
+  MsmPlan plan;
+  PhaseTimer pt(ctx->profiling, st);
+  if ((rc = msm_begin<CF>(ctx, n, n, st, &plan))) return rc;
+  if ((rc = msm_slice<CF, SF>(ctx, &plan, d_scalars, 0, n, false, st, &pt))) return rc;
+  if ((rc = msm_finish<CF>(ctx, &plan, st, &pt))) return rc;
   if (ctx->profiling) {
     CU(cudaStreamSynchronize(st));
     ctx->stats.ms_digits = pt.ms(0, 1);
@@ -182,16 +221,55 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
   return MIRA_OK;
 }
 
+// Scalars in HOST memory: the vector is cut into slices; slice k+1 crosses PCIe on the copy stream while slice k
+// runs digits -> sort -> accumulate, so only the first slice's copy is exposed.  (Pageable host memory makes
+// cudaMemcpyAsync synchronous, which degrades this to copy-then-compute; pinned buffers get the overlap.)
+constexpr int SLICE_MAX_COUNT = 4;                 // ctx->slice_min: do not cut below that many scalars per slice
+
+template <class CF, class SF>
+int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st) {
+  int rc;
+  if ((rc = ctx->result.ensure(256))) return rc;
+  if (n == 0) {
+    CU(cudaMemsetAsync(ctx->result.p, 0, 128, st));
+    ctx->stats = mira_msm_stats{};
+    return MIRA_OK;
+  }
+  if ((rc = ctx->scalars.ensure(n * 32))) return rc;
+  int K = (int)(n / (ctx->slice_min ? ctx->slice_min : 1));
+  K = K < 1 ? 1 : (K > SLICE_MAX_COUNT ? SLICE_MAX_COUNT : K);
+  size_t per = ((n + K - 1) / K + 255) & ~(size_t)255;
+  if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < SLICE_MAX_COUNT; k++)
+    if (!ctx->copy_done[k]) CU(cudaEventCreateWithFlags(&ctx->copy_done[k], cudaEventDisableTiming));
+  if (!ctx->compute_idle) CU(cudaEventCreateWithFlags(&ctx->compute_idle, cudaEventDisableTiming));
+  // the copies must not overtake work already queued on `st` that still reads ctx->scalars (a previous commit)
+  CU(cudaEventRecord(ctx->compute_idle, st));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_idle, 0));
+  int n_slices = 0;
+  for (size_t first = 0; first < n; first += per, n_slices++) {
+    size_t cnt = n - first < per ? n - first : per;
+    CU(cudaMemcpyAsync((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, cudaMemcpyHostToDevice,
+                       ctx->copy_stream));
+    CU(cudaEventRecord(ctx->copy_done[n_slices], ctx->copy_stream));
+  }
+  MsmPlan plan;
+  if ((rc = msm_begin<CF>(ctx, n, per < n ? per : n, st, &plan))) return rc;
+  int k = 0;
+  for (size_t first = 0; first < n; first += per, k++) {
+    size_t cnt = n - first < per ? n - first : per;
+    CU(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
+    if ((rc = msm_slice<CF, SF>(ctx, &plan, (const char*)ctx->scalars.p + first * 32, first, cnt, k > 0, st, nullptr))) return rc;
+  }
+  return msm_finish<CF>(ctx, &plan, st, nullptr);
+}
+
 template <class CF, class SF>
 int commit_impl(mira_msm_ctx* ctx, const void* scalars, size_t n, int on_device, void* out, bool want_affine, cudaStream_t st) {
   int rc;
-  const void* d_scalars = scalars;
-  if (!on_device && n) {
-    if ((rc = ctx->scalars.ensure(n * 32))) return rc;
-    CU(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    d_scalars = ctx->scalars.p;
-  }
-  if ((rc = msm_device<CF, SF>(ctx, d_scalars, n, st))) return rc;
+  if (on_device) rc = msm_device<CF, SF>(ctx, scalars, n, st);
+  else rc = msm_host<CF, SF>(ctx, scalars, n, st);
+  if (rc) return rc;
   if (want_affine) {
     k_finalize<CF><<<1, 32, 0, st>>>(ctx->result.p, (char*)ctx->result.p + 128);
     ctx->stats.kernel_launches++;

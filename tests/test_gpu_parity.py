@@ -262,3 +262,31 @@ def test_key_file_roundtrip(gpu, tmp_path):
     path.write_bytes(bytes(bad))
     with pytest.raises(NotOnCurve):
         CommitmentKey.load_or_setup_cache(str(tmp_path), "bn256", k, BN254_G1)
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+@pytest.mark.parametrize("dist", [0, 1])
+def test_sliced_host_commit_equals_unsliced(gpu, curve, dist):
+    """Host-buffer commits fold the scalar vector into the buckets slice by slice (H2D overlap); the result must
+    not depend on the slicing.  Slices of 1000 scalars force 4 ragged slices at these sizes."""
+    from mira_b200 import CommitmentKey, combine_partials
+    for n in (999, 4001, 70_001):
+        bases = O.gen_bases(curve, 21, n)
+        sc = O.gen_scalars(curve, 22 + n, n, dist)
+        ck = CommitmentKey(curve, bases)
+        ck.set_slice_min(0)
+        whole = ck.commit(sc)
+        for c in (0, 6, 13):
+            ck.set_window(c)
+            ck.set_slice_min(1000)
+            assert ck.commit(sc) == whole
+            assert combine_partials(curve, ck.partial(sc)) == whole
+        ck.set_window(0)
+        assert whole == O.commit(curve, bases, sc)
+    # one heavy bucket: every scalar equal => a single run spanning every chunk of every slice
+    n = 50_000
+    bases = O.gen_bases(curve, 23, n)
+    one = O.gen_scalars(curve, 5, 1, 0) * n
+    ck = CommitmentKey(curve, bases)
+    ck.set_slice_min(5000)
+    assert ck.commit(one) == O.commit(curve, bases, one)
