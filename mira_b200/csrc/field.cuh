@@ -131,18 +131,87 @@ template <class F> __device__ __forceinline__ Fe<F> fe_from_canonical(const Fe<F
   return fe_mul(a, r2);
 }
 
-// a^(m-2) by square-and-multiply over the (compile-time) modulus bits.  0 -> 0.
+// ---- inversion -----------------------------------------------------------------------------------
+// Plain 256-bit helpers for the binary extended Euclid below (values < 2^255, so no carry out of limb 7).
+__device__ __forceinline__ void u256_shr1(uint32_t (&a)[8]) {
+#pragma unroll
+  for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+  a[7] >>= 1;
+}
+__device__ __forceinline__ void u256_add(uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a[i] + b[i];
+    a[i] = (uint32_t)c;
+    c >>= 32;
+  }
+}
+__device__ __forceinline__ uint32_t u256_sub(uint32_t (&a)[8], const uint32_t (&b)[8]) {   // returns the borrow
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)a[i] - b[i] - br;
+    a[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+  return (uint32_t)br;
+}
+__device__ __forceinline__ bool u256_ge(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {
+    if (a[i] != b[i]) return a[i] > b[i];
+  }
+  return true;
+}
+__device__ __forceinline__ bool u256_is_one(const uint32_t (&a)[8]) {
+  uint32_t o = a[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < 8; i++) o |= a[i];
+  return o == 0;
+}
+
+// 1/a in Montgomery form; 0 -> 0 (as Field::invert().unwrap_or(0) is used by Curve::to_affine).
+// Binary extended Euclid on the raw residue: shifts, adds and subtracts only, i.e. ~500 short iterations on the
+// ALU pipe instead of the ~380 dependent Montgomery products of a Fermat ladder (0.6 ms on one thread).
+// With A = a*R the loop yields A^{-1} = a^{-1} R^{-1}; two products by R^2 bring it to a^{-1} R.
 template <class F> __device__ __noinline__ Fe<F> fe_inv(const Fe<F>& a) {
-  Fe<F> acc = fe_one<F>();
-  // exponent = MOD - 2 (MOD is odd and its low word is > 2 for both fields)
-  for (int w = 7; w >= 0; w--) {
-    uint32_t e = FieldParams<F>::mod(w) - (w == 0 ? 2u : 0u);
-    for (int b = 31; b >= 0; b--) {
-      acc = fe_sqr(acc);
-      if ((e >> b) & 1u) acc = fe_mul(acc, a);
+  if (fe_is_zero(a)) return a;
+  uint32_t u[8], v[8], x1[8], x2[8], p[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u[i] = a.v[i];
+    p[i] = v[i] = FieldParams<F>::mod(i);
+    x1[i] = (i == 0);
+    x2[i] = 0;
+  }
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+    while (!(u[0] & 1u)) {
+      u256_shr1(u);
+      if (x1[0] & 1u) u256_add(x1, p);
+      u256_shr1(x1);
+    }
+    while (!(v[0] & 1u)) {
+      u256_shr1(v);
+      if (x2[0] & 1u) u256_add(x2, p);
+      u256_shr1(x2);
+    }
+    if (u256_ge(u, v)) {
+      u256_sub(u, v);
+      if (u256_sub(x1, x2)) u256_add(x1, p);
+    } else {
+      u256_sub(v, u);
+      if (u256_sub(x2, x1)) u256_add(x2, p);
     }
   }
-  return acc;
+  Fe<F> r, r2;
+  const bool from_u = u256_is_one(u);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.v[i] = from_u ? x1[i] : x2[i];
+    r2.v[i] = FieldParams<F>::r2(i);
+  }
+  return fe_mul(fe_mul(r, r2), r2);
 }
 
 // ---- 128-bit vectorised global-memory access (elements are 32-byte aligned in all our buffers)

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__
 // pairs into a few buckets) is not walked serially: its leader chunk is appended to `heavy` and
 // k_combine_heavy folds its pieces with a whole block.
 constexpr uint32_t HEAVY_CHUNKS = 8;
+constexpr uint32_t HUGE_CHUNKS = 256;     // runs spanning more chunks than this get a whole block, the rest a warp
 
 template <class CF>
 __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ skeys,
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ sk
                                                  const uint32_t* __restrict__ n_ptr, int L,
                                                  void* __restrict__ buckets, uint32_t* __restrict__ heavy,
                                                  uint32_t heavy_cap) {
+  // heavy = [count_medium, count_huge, medium leaders (heavy_cap), huge leaders (heavy_cap)]
   const uint32_t n = *n_ptr;
   const uint32_t n_chunks = (n + L - 1) / L;
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,9 +192,11 @@ __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ sk
   {
     uint64_t probe = (uint64_t)(chunk + HEAVY_CHUNKS) * (uint32_t)L;
     if (probe < n && skeys[probe] == (pk & PK_KEY_MASK)) {
-      uint32_t slot = atomicAdd(&heavy[0], 1u);
+      uint64_t probe2 = (uint64_t)(chunk + HUGE_CHUNKS) * (uint32_t)L;
+      bool huge = probe2 < n && skeys[probe2] == (pk & PK_KEY_MASK);
+      uint32_t slot = atomicAdd(&heavy[huge ? 1 : 0], 1u);
       if (slot < heavy_cap) {            // heavy_cap >= n_chunks / HEAVY_CHUNKS + 1: cannot overflow
-        heavy[1 + slot] = q;
+        heavy[2 + (huge ? heavy_cap : 0u) + slot] = q;
         return;
       }
     }
@@ -208,11 +212,12 @@ __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ sk
   xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)(pk & PK_KEY_MASK) * 128, acc);
 }
 
-// One block per heavy run (grid-stride over the heavy list).  The run's pieces are the leader slot q0 and
-// slot 0 of chunks t0+1 .. t1, where t1 is the last chunk whose first pair still carries the key (binary
-// search over the sorted keys).  Threads sum pieces strided, then a shared-memory tree folds the block.
+// Heavy runs.  The run's pieces are the leader slot q0 and slot 0 of chunks t0+1 .. t1, where t1 is the last chunk
+// whose first pair still carries the key (binary search over the sorted keys).  GROUP threads (a warp for runs of
+// up to HUGE_CHUNKS chunks - e.g. the top window, whose few significant bits put thousands of pairs into each of
+// a few thousand buckets - or a whole block beyond that) sum the pieces strided, then fold through shared memory.
 constexpr int HV_THREADS = 256;
-template <class CF>
+template <class CF, int GROUP>
 __global__ void __launch_bounds__(HV_THREADS) k_combine_heavy(const uint32_t* __restrict__ skeys,
                                                               const uint32_t* __restrict__ part_keys,
                                                               const void* __restrict__ part_pts,
@@ -220,38 +225,49 @@ __global__ void __launch_bounds__(HV_THREADS) k_combine_heavy(const uint32_t* __
                                                               void* __restrict__ buckets,
                                                               const uint32_t* __restrict__ heavy, uint32_t heavy_cap) {
   __shared__ uint4 sm[HV_THREADS * 8];
+  constexpr int GROUPS = HV_THREADS / GROUP;
   const uint32_t n = *n_ptr;
   const uint32_t n_chunks = (n + L - 1) / L;
-  uint32_t n_heavy = heavy[0] < heavy_cap ? heavy[0] : heavy_cap;
-  for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
-    const uint32_t q0 = heavy[1 + h];
-    const uint32_t key = part_keys[q0] & PK_KEY_MASK;
-    const uint32_t t0 = q0 >> 1;
-    // t1 = largest chunk index with skeys[t1 * L] == key  (keys are sorted, chunk t0+1 qualifies)
-    uint32_t lo = t0 + 1, hi = n_chunks - 1;
-    while (lo < hi) {
-      uint32_t mid = lo + (hi - lo + 1) / 2;
-      if (skeys[(uint64_t)mid * (uint32_t)L] <= key) lo = mid; else hi = mid - 1;
-    }
-    const uint32_t t1 = lo;
+  const uint32_t which = GROUP == HV_THREADS ? 1u : 0u;
+  const uint32_t* list = heavy + 2 + which * heavy_cap;
+  uint32_t n_heavy = heavy[which] < heavy_cap ? heavy[which] : heavy_cap;
+  const uint32_t g = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+  // every group of a block runs the same number of iterations (block-wide barriers below)
+  const uint32_t iters = (n_heavy + gridDim.x * GROUPS - 1) / (gridDim.x * GROUPS);
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t h = (it * gridDim.x + blockIdx.x) * GROUPS + g;
+    const bool active = h < n_heavy;
     Xyzz<CF> acc = xyzz_identity<CF>();
-    if (threadIdx.x == 0) acc = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)q0 * 128);
-    for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += HV_THREADS) {
-      Xyzz<CF> p = xyzz_load<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)(2 * t) * 128);
-      xyzz_add(acc, p);
+    uint32_t key = 0;
+    if (active) {
+      const uint32_t q0 = list[h];
+      key = part_keys[q0] & PK_KEY_MASK;
+      const uint32_t t0 = q0 >> 1;
+      // t1 = largest chunk index with skeys[t1 * L] == key  (keys are sorted, chunk t0+1 qualifies)
+      uint32_t lo = t0 + 1, hi = n_chunks - 1;
+      while (lo < hi) {
+        uint32_t mid = lo + (hi - lo + 1) / 2;
+        if (skeys[(uint64_t)mid * (uint32_t)L] <= key) lo = mid; else hi = mid - 1;
+      }
+      const uint32_t t1 = lo;
+      if (lane == 0) acc = xyzz_load_shared<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)q0 * 128);
+      for (uint32_t t = t0 + 1 + lane; t <= t1; t += GROUP) {
+        Xyzz<CF> p = xyzz_load_shared<CF>(reinterpret_cast<const char*>(part_pts) + (size_t)(2 * t) * 128);
+        xyzz_add(acc, p);
+      }
     }
     char* my = reinterpret_cast<char*>(sm) + threadIdx.x * 128;
     xyzz_store<CF>(my, acc);
     __syncthreads();
-    for (int s = HV_THREADS >> 1; s > 0; s >>= 1) {
-      if ((int)threadIdx.x < s) {
+    for (int s = GROUP >> 1; s > 0; s >>= 1) {
+      if ((int)lane < s) {
         Xyzz<CF> o = xyzz_load_shared<CF>(reinterpret_cast<char*>(sm) + (threadIdx.x + s) * 128);
         xyzz_add(acc, o);
         xyzz_store<CF>(my, acc);
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)key * 128, acc);
+    if (active && lane == 0) xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)key * 128, acc);
     __syncthreads();
   }
 }

@@ -149,14 +149,16 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, size_t fi
     k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(skeys, srefs, d_npairs, L, tab->d, ctx->buckets.p,
                                                             (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
     uint32_t heavy_cap = n_chunks / HEAVY_CHUNKS + 2;
-    if ((rc = ctx->cursor.ensure(((size_t)heavy_cap + 2) * 4))) return rc;
-    uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0] = count, [1..] = leader slots of heavy runs
-    CU(cudaMemsetAsync(d_heavy, 0, 4, st));
+    if ((rc = ctx->cursor.ensure(((size_t)heavy_cap * 2 + 4) * 4))) return rc;
+    uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0], [1] = counts, then the medium and the huge leader lists
+    CU(cudaMemsetAsync(d_heavy, 0, 8, st));
     k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
                                                              ctx->buckets.p, d_heavy, heavy_cap);
-    k_combine_heavy<CF><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
-                                                       ctx->buckets.p, d_heavy, heavy_cap);
-    plan->launches += 3;
+    k_combine_heavy<CF, 32><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
+                                                           ctx->buckets.p, d_heavy, heavy_cap);
+    k_combine_heavy<CF, HV_THREADS><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs,
+                                                                   L, ctx->buckets.p, d_heavy, heavy_cap);
+    plan->launches += 4;
   }
   if (pt) pt->mark(3);
   plan->entries += E;
