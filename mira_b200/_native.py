@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmira_b200.so")
+# MIRA_B200_LIB selects an A/B build of the same sources (mira_b200/csrc/Makefile VARIANT=...); never a fallback
+LIB_PATH = os.environ.get("MIRA_B200_LIB") or os.path.join(_HERE, "libmira_b200.so")
 
 MIRA_OK = 0
 MIRA_ERR_TOO_LONG_INPUT = -1

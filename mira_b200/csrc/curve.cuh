@@ -128,7 +128,7 @@ template <class F> __device__ __forceinline__ void xyzz_madd(Xyzz<F>& acc, const
   Fe<F> ppp = fe_mul(p, pp);
   Fe<F> qq = fe_mul(acc.x, pp);
   Fe<F> x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fe<F> y3 = fe_sub(fe_mul(r, fe_sub(qq, x3)), fe_mul(acc.y, ppp));
+  Fe<F> y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fe_mul(acc.zz, pp);
@@ -154,7 +154,7 @@ template <class F> __device__ __forceinline__ void xyzz_add(Xyzz<F>& acc, const 
   Fe<F> ppp = fe_mul(p, pp);
   Fe<F> qq = fe_mul(u1, pp);
   Fe<F> x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fe<F> y3 = fe_sub(fe_mul(r, fe_sub(qq, x3)), fe_mul(s1, ppp));
+  Fe<F> y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fe_mul(fe_mul(acc.zz, q.zz), pp);

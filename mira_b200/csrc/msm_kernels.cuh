@@ -111,8 +111,11 @@ __device__ __forceinline__ Affine<CF> load_ref(const void* __restrict__ table, u
   return p;
 }
 
+#ifndef MIRA_ACC_MIN_BLOCKS
+#define MIRA_ACC_MIN_BLOCKS 1
+#endif
 template <class CF>
-__global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ skeys,
+__global__ void __launch_bounds__(128, MIRA_ACC_MIN_BLOCKS) k_accumulate(const uint32_t* __restrict__ skeys,
                                                     const uint32_t* __restrict__ srefs,
                                                     const uint32_t* __restrict__ n_ptr, int L,
                                                     const void* __restrict__ table, void* __restrict__ buckets,

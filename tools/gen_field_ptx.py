@@ -51,8 +51,9 @@ class Prog:
 
     # helpers -----------------------------------------------------------
     def mul_wide(self, lo, hi, a, b):
-        self.op("mul.lo.u32", lo, a, b)
-        self.op("mul.hi.u32", hi, a, b)
+        # one mul.wide.u32 (-> IMAD.WIDE.U32) instead of a mul.lo/mul.hi pair, which ptxas does NOT fuse: it emits
+        # IMAD + IMAD.HI.U32, and IMAD.HI issues slower than IMAD.WIDE on B200 (profiles/r01_intpipe_microbench.jsonl)
+        self.op("mul.wide.u32", (lo, hi), a, b)
 
     def mad_chain(self, acc, a_list, b, carry_in=False, top=None, acc_in=None):
         """acc[2k],acc[2k+1] (+)= a_list[k]*b for k in range(len), carries chained.
@@ -88,14 +89,14 @@ def build_mont_mul(mod: int, square: bool = False) -> Prog:
     od = [p.reg("o") for _ in range(N + 1)]   # odd-aligned row, word k at position k+1
     m = p.reg("m")
 
-    # ---- row 0: plain products
-    for k in range(4):
-        p.mul_wide(ev[2 * k], ev[2 * k + 1], a_even[k], b[0])
-    for k in range(4):
-        p.mul_wide(od[2 * k], od[2 * k + 1], a_odd[k], b[0])
+    # ---- row 0: products written as carry chains over a zero addend.  A mul.lo/mul.hi pair (or mul.wide.u32) is
+    # split by ptxas into IMAD + IMAD.HI.U32, which issues slower than the IMAD.WIDE.U32 the chain form fuses into.
+    zeros = [None] * (N + 1)
+    p.mad_chain(ev, a_even, b[0], acc_in=zeros, top=(ev[8], None))
+    p.mad_chain(od, a_odd, b[0], acc_in=zeros, top=(od[8], None))
     p.op("mul.lo.u32", m, ev[0], n0inv)
-    p.mad_chain(od, m_odd_regs(m_odd), m, top=(od[8], None))
-    p.mad_chain(ev, m_odd_regs(m_even), m, top=(ev[8], None))
+    p.mad_chain(od, m_odd_regs(m_odd), m, top=(od[8], od[8]))
+    p.mad_chain(ev, m_odd_regs(m_even), m, top=(ev[8], ev[8]))
     # ---- rows 1..7
     for i in range(1, N):
         # divide by 2^32: ev[0] is zero, ev[1] is a lone word at the new position 0,
@@ -133,6 +134,60 @@ def build_mont_mul(mod: int, square: bool = False) -> Prog:
 
 def m_odd_regs(lst):
     return list(lst)
+
+
+def build_mont_mul2(mod: int) -> Prog:
+    """r = (a*b + c*d) / 2^256 mod `mod`: TWO products under ONE Montgomery reduction (192 wide MACs instead of 256).
+    Inputs < mod, output < mod.  Registers: a0..a7, b0..b7, c0..c7 (named b8..b15), d0..d7 (b16..b23) -> r0..r7.
+    Bound: the accumulator stays below 2*mod^2/2^256 + mod < 2*mod (mod < 2^254), so one conditional subtraction."""
+    p = Prog()
+    n0inv = (-pow(mod, -1, W)) % W
+    ml = limbs(mod)
+    a = [f"a{i}" for i in range(N)]
+    b = [f"b{i}" for i in range(N)]
+    c = [f"b{8 + i}" for i in range(N)]
+    d = [f"b{16 + i}" for i in range(N)]
+    a_even, a_odd, c_even, c_odd = a[0::2], a[1::2], c[0::2], c[1::2]
+    m_even, m_odd = ml[0::2], ml[1::2]
+    ev = [p.reg("e") for _ in range(N + 1)]
+    od = [p.reg("o") for _ in range(N + 1)]
+    m = p.reg("m")
+    zeros = [None] * (N + 1)
+    p.mad_chain(ev, a_even, b[0], acc_in=zeros, top=(ev[8], None))
+    p.mad_chain(od, a_odd, b[0], acc_in=zeros, top=(od[8], None))
+    p.mad_chain(od, c_odd, d[0], top=(od[8], od[8]))
+    p.mad_chain(ev, c_even, d[0], top=(ev[8], ev[8]))
+    p.op("mul.lo.u32", m, ev[0], n0inv)
+    p.mad_chain(od, m_odd, m, top=(od[8], od[8]))
+    p.mad_chain(ev, m_even, m, top=(ev[8], ev[8]))
+    for i in range(1, N):
+        pend = ev[1]
+        old_ev = ev
+        new_ev = od
+        new_od = [p.reg("o") for _ in range(N + 1)]
+        shifted = [old_ev[2 + k] if 2 + k <= N else None for k in range(N)]
+        p.op("add.cc.u32", new_ev[0], new_ev[0], pend)
+        p.mad_chain(new_od, a_odd, b[i], carry_in=True, acc_in=shifted, top=(new_od[8], None))
+        p.mad_chain(new_ev, a_even, b[i], top=(new_ev[8], new_ev[8]))
+        p.mad_chain(new_od, c_odd, d[i], top=(new_od[8], new_od[8]))
+        p.mad_chain(new_ev, c_even, d[i], top=(new_ev[8], new_ev[8]))
+        p.op("mul.lo.u32", m, new_ev[0], n0inv)
+        p.mad_chain(new_od, m_odd, m, top=(new_od[8], new_od[8]))
+        p.mad_chain(new_ev, m_even, m, top=(new_ev[8], new_ev[8]))
+        ev, od = new_ev, new_od
+    t = [p.reg("v") for _ in range(N)]
+    p.op("add.cc.u32", t[0], od[0], ev[1])
+    for k in range(1, N):
+        p.op("addc.cc.u32" if k < N - 1 else "addc.u32", t[k], od[k], ev[k + 1])
+    s = [p.reg("s") for _ in range(N)]
+    brw = p.reg("w")
+    p.op("sub.cc.u32", s[0], t[0], ml[0])
+    for k in range(1, N):
+        p.op("subc.cc.u32", s[k], t[k], ml[k])
+    p.op("subc.u32", brw, 0, 0)
+    for k in range(N):
+        p.op("selp_nz", f"r{k}", t[k], s[k], brw)
+    return p
 
 
 def build_add(mod: int) -> Prog:
@@ -183,7 +238,10 @@ def simulate(prog: Prog, inputs: dict) -> dict:
 
     for name, dst, src in prog.ops:
         s = [val(x) for x in src]
-        if name == "mul.lo.u32":
+        if name == "mul.wide.u32":
+            regs[dst[0]] = (s[0] * s[1]) & M32
+            regs[dst[1]] = (s[0] * s[1]) >> 32
+        elif name == "mul.lo.u32":
             regs[dst] = (s[0] * s[1]) & M32
         elif name == "mul.hi.u32":
             regs[dst] = (s[0] * s[1]) >> 32
@@ -239,8 +297,28 @@ def selftest():
                 got = sum(out[f"r{i}"] << (32 * i) for i in range(N))
                 want = x * y * rinv % mod
                 assert got == want, (fname, square, hex(x), hex(y), hex(got), hex(want))
-            nwide = sum(1 for o in prog.ops if o[0] in ("mul.lo.u32", "mad.lo.cc.u32", "madc.lo.cc.u32")) - N
+            nwide = sum(1 for o in prog.ops if o[0] in ("mul.wide.u32", "mad.lo.cc.u32", "madc.lo.cc.u32"))
             print(f"selftest {fname} square={square}: {len(cases)} cases ok; ops={len(prog.ops)} wideMACs={nwide}")
+
+
+def selftest_mul2():
+    rng = random.Random(99)
+    for fname, mod in FIELDS.items():
+        prog = build_mont_mul2(mod)
+        rinv = pow(1 << 256, -1, mod)
+        edge = [0, 1, mod - 1, mod - 2, (1 << 253), (W << 224) % mod]
+        cases = [(x, y, z, w) for x in edge for y in edge for z in edge for w in edge]
+        cases += [tuple(rng.randrange(mod) for _ in range(4)) for _ in range(4000)]
+        for x, y, z, w in cases:
+            inp = {f"a{i}": v for i, v in enumerate(limbs(x))}
+            inp.update({f"b{i}": v for i, v in enumerate(limbs(y))})
+            inp.update({f"b{8 + i}": v for i, v in enumerate(limbs(z))})
+            inp.update({f"b{16 + i}": v for i, v in enumerate(limbs(w))})
+            out = simulate(prog, inp)
+            got = sum(out[f"r{i}"] << (32 * i) for i in range(N))
+            assert got == (x * y + z * w) * rinv % mod, (fname, hex(x), hex(y), hex(z), hex(w))
+        nwide = sum(1 for o in prog.ops if o[0] in ("mul.wide.u32", "mad.lo.cc.u32", "madc.lo.cc.u32"))
+        print(f"selftest {fname} mul2 (a*b + c*d): {len(cases)} cases ok; ops={len(prog.ops)} wideMACs={nwide}")
 
 
 def selftest_addsub():
@@ -260,12 +338,14 @@ def selftest_addsub():
 
 
 # ------------------------------------------------------------------ PTX emission
-def emit_function(name: str, prog: Prog, square: bool) -> str:
+def emit_function(name: str, prog: Prog, square: bool, n_b: int = N) -> str:
     # collect temporaries
     temps = []
     seen = set()
+    n_wide = sum(1 for o in prog.ops if o[0] == "mul.wide.u32")
     for _, dst, src in prog.ops:
-        for x in (dst,) + tuple(src):
+        dsts = dst if isinstance(dst, tuple) else (dst,)
+        for x in dsts + tuple(src):
             if isinstance(x, str) and not (x[0] in "abr" and x[1:].isdigit()) and x not in seen:
                 seen.add(x)
                 temps.append(x)
@@ -281,8 +361,15 @@ def emit_function(name: str, prog: Prog, square: bool) -> str:
             return f"%{16 + int(x[1:])}"
         return x
     lines = ["{", ".reg .u32 " + ", ".join(temps) + ";", ".reg .pred pb;"]
+    if n_wide:
+        lines.append(".reg .u64 " + ", ".join(f"wd{i}" for i in range(n_wide)) + ";")
+    wide_ix = 0
     for opn, dst, src in prog.ops:
-        if opn == "selp_nz":
+        if opn == "mul.wide.u32":
+            lines.append(f"mul.wide.u32 wd{wide_ix}, {ref(src[0])}, {ref(src[1])};")
+            lines.append(f"mov.b64 {{{ref(dst[0])}, {ref(dst[1])}}}, wd{wide_ix};")
+            wide_ix += 1
+        elif opn == "selp_nz":
             lines.append(f"setp.ne.u32 pb, {ref(src[2])}, 0;")
             lines.append(f"selp.u32 {ref(dst)}, {ref(src[0])}, {ref(src[1])}, pb;")
         elif opn == "addc.u32_wrap":
@@ -294,8 +381,8 @@ def emit_function(name: str, prog: Prog, square: bool) -> str:
     outs = ", ".join(f'"=r"(r[{i}])' for i in range(N))
     ins = ", ".join(f'"r"(a[{i}])' for i in range(N))
     if not square:
-        ins += ", " + ", ".join(f'"r"(b[{i}])' for i in range(N))
-    sig = "uint32_t (&r)[8], const uint32_t (&a)[8]" + ("" if square else ", const uint32_t (&b)[8]")
+        ins += ", " + ", ".join(f'"r"(b[{i}])' for i in range(n_b))
+    sig = "uint32_t (&r)[8], const uint32_t (&a)[8]" + ("" if square else f", const uint32_t (&b)[{n_b}]")
     return (f"__device__ __forceinline__ void {name}({sig}) {{\n"
             f"  uint32_t t0, t1, t2, t3, t4, t5, t6, t7;\n"
             f"  asm(\n{body}\n"
@@ -312,6 +399,7 @@ def emit_cuda(path: str):
     for fname, mod in FIELDS.items():
         out.append(emit_function(f"mont_mul_{fname}", build_mont_mul(mod, False), False))
         out.append(emit_function(f"mont_sqr_{fname}", build_mont_mul(mod, True), True))
+        out.append(emit_function(f"mont_mul2_{fname}", build_mont_mul2(mod), False, n_b=24))
         out.append(emit_function(f"mod_add_{fname}", build_add(mod), False))
         out.append(emit_function(f"mod_sub_{fname}", build_sub(mod), False))
     out.append("} }  // namespace mira::gen")
@@ -322,6 +410,7 @@ def emit_cuda(path: str):
 
 if __name__ == "__main__":
     selftest()
+    selftest_mul2()
     selftest_addsub()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     emit_cuda(os.path.join(root, "mira_b200", "csrc", "field_gen.cuh"))
