@@ -34,7 +34,8 @@ SEED_BASES = 0x4D495241          # "MIRA"
 SEED_SCALARS = 0x4D495242
 IMAD_WIDE_PER_CLK_PER_SM = 32    # measured, profiles/r01_intpipe_microbench.jsonl
 MACS_PER_MODMUL = 136            # 8-limb CIOS: 2*8^2 + 8
-MODMUL_PER_MADD = 10             # XYZZ mixed add 8M + 2S
+MODMUL_PER_MADD = 10             # XYZZ mixed add 8M + 2S (canonical count: 1,360 wide MACs per pair)
+MACS_PER_MADD_EXECUTED = 8 * 136 + 200   # 8 products + one dual product a*b + c*d under a single reduction (192 + 8)
 ACC_DRAM_BYTES_PER_PAIR = 29.09e9 / 201326592   # measured, profiles/r01_accumulate_v3.txt
 
 
@@ -207,7 +208,8 @@ def run_ours(args):
     # (point, window) entry.  Its binding resource is the integer pipe (IMAD.WIDE.U32), reported beside it.
     acc_s = prof["ms_accumulate"] * 1e-3
     alg_bytes = entries * 72.0
-    macs = entries * MODMUL_PER_MADD * MACS_PER_MODMUL
+    macs = entries * MACS_PER_MADD_EXECUTED
+    macs_canonical = entries * MODMUL_PER_MADD * MACS_PER_MODMUL
     imad_peak = 148 * IMAD_WIDE_PER_CLK_PER_SM * sm_max * 1e6
     out = {
         "metric": "BN254 G1 MSM Mpoints/s" if curve == 0 else "Grumpkin G1 MSM Mpoints/s",
@@ -234,6 +236,9 @@ def run_ours(args):
                      "note": "kernel is integer-pipe bound, see roofline_imad"},
         "roofline_imad": {"kernel": "k_accumulate (+k_combine)", "bound": "imad.wide.u32", "achieved": round(macs / acc_s / 1e12, 3),
                           "peak": round(imad_peak / 1e12, 3), "unit": "T wide-MAC/s", "frac": round(macs / acc_s / imad_peak, 4),
+                          "achieved_canonical": round(macs_canonical / acc_s / 1e12, 3),
+                          "note": "achieved = wide MACs actually executed (1,288 per pair); achieved_canonical uses SURVEY.md "
+                                  "8d's 10 x 136 = 1,360 per pair",
                           "peak_source": "measured 32 IMAD.WIDE.U32 lanes/clk/SM x 148 SMs x max SM clock"},
     }
     if world == 1 and not args.no_cpu_baseline:
