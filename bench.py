@@ -118,7 +118,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: ONE JSON line
+        # NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION (WARN included); the contract is ONE
+        # JSON line, so run it silent unless the caller asks for NCCL logs explicitly
+        if "MIRA_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["MIRA_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     curve = curve_id(args.curve)
     n = 1 << args.log_n                      # points per rank

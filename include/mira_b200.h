@@ -161,6 +161,11 @@ typedef struct {
  * Index errors the reference raises per row are raised here once, when the program is bound to the domain. */
 int mira_eval_rows(const mira_eval_program *prog, const mira_eval_domain *dom, void *out_dev, int device,
                    void *stream);
+/* The same for rows [row_begin, row_end) only; out_dev holds row_end - row_begin elements.  This is the row-range
+ * shard of SURVEY.md 8e: each rank evaluates its range (rotations still read the whole, read-only columns) and
+ * commits it against its slice of the key; row_end > row_size is RowIndexOutOfBoundary. */
+int mira_eval_rows_range(const mira_eval_program *prog, const mira_eval_domain *dom, uint64_t row_begin,
+                         uint64_t row_end, void *out_dev, int device, void *stream);
 typedef struct {
   uint32_t instructions;   /* device instructions after Store-forwarding and Horner expansion */
   uint32_t slots;          /* live intermediates kept per row (local memory) */

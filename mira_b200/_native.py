@@ -29,7 +29,7 @@ SYMBOLS = [
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_msm_set_slice_min", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
-    "mira_eval_rows", "mira_eval_program_stats", "mira_fft", "mira_fft_std", "mira_test_eval_link",
+    "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_fft", "mira_fft_std", "mira_test_eval_link",
 ]
 _VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy")
 
@@ -102,6 +102,7 @@ def lib():
     L.mira_eval_program_destroy.argtypes = [vp]
     L.mira_eval_program_destroy.restype = None
     L.mira_eval_rows.argtypes = [vp, C.POINTER(EvalDomain), vp, i, vp]
+    L.mira_eval_rows_range.argtypes = [vp, C.POINTER(EvalDomain), C.c_uint64, C.c_uint64, vp, i, vp]
     L.mira_eval_program_stats.argtypes = [vp, C.POINTER(EvalStats)]
     u32p = C.POINTER(C.c_uint32)
     L.mira_test_eval_link.argtypes = [vp, C.POINTER(EvalDomain), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), u32p, u32p, u32p]

@@ -30,18 +30,15 @@ constexpr uint32_t PK_KEY_MASK = 0x3fffffffu;
 constexpr int DG_THREADS = 256;
 constexpr int DG_WARPS = DG_THREADS / 32;
 
-__device__ __forceinline__ uint32_t signed_digit(const uint32_t (&s)[8], int j, int c, uint32_t& carry, uint32_t& neg) {
+// digit j of the canonical scalar whose 8 limbs (+ a zero 9th) sit in shared memory at `sc` (stride-9 rows are
+// bank-conflict free): two LDS and a funnel shift instead of a register-select ladder
+__device__ __forceinline__ uint32_t signed_digit(const uint32_t* sc, int j, int c, uint32_t& carry, uint32_t& neg) {
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (1u << c) - 1u;     // c <= 26
   int bit = j * c;
   int w = bit >> 5, sh = bit & 31;
-  uint32_t lo = 0, hi = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {             // register-resident select instead of dynamic indexing
-    if (k == w) lo = s[k];
-    if (k == w + 1) hi = s[k];
-  }
-  uint32_t d = (sh ? ((lo >> sh) | (hi << (32 - sh))) : lo) & mask;
+  uint32_t lo = w < 8 ? sc[w] : 0u, hi = w < 7 ? sc[w + 1] : 0u;
+  uint32_t d = __funnelshift_r(lo, hi, sh) & mask;
   d += carry;
   neg = 0;
   carry = 0;
@@ -57,36 +54,56 @@ template <class SF>
 __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ scalars, uint32_t n, uint32_t first, int c, int W,
                                                        uint32_t n_cover, uint32_t* __restrict__ keys,
                                                        uint32_t* __restrict__ refs, uint32_t* __restrict__ n_out) {
-  extern __shared__ uint32_t sm_cnt[];       // [W][DG_WARPS] pair counts -> offsets, then [0] = block base
+  extern __shared__ uint32_t sm_cnt[];       // [W][DG_WARPS] pair counts -> exclusive offsets
+  __shared__ uint32_t sm_sc[DG_THREADS * 9];
   __shared__ uint32_t sm_base;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool valid = i < n;
   Fe<SF> s = fe_zero<SF>();
   if (valid) s = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + (size_t)i * 32));
+  uint32_t* sc = sm_sc + threadIdx.x * 9;
+#pragma unroll
+  for (int k = 0; k < 8; k++) sc[k] = s.v[k];
   // pass 1: count the non-zero digits per (window, warp)
   uint32_t carry = 0, neg;
   for (int j = 0; j < W; j++) {
-    uint32_t d = signed_digit(s.v, j, c, carry, neg);
+    uint32_t d = signed_digit(sc, j, c, carry, neg);
     uint32_t b = __ballot_sync(0xffffffffu, d != 0);
     if (lane == 0) sm_cnt[j * DG_WARPS + warp] = __popc(b);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {                    // W*8 <= 1024 values: a serial scan is cheap next to W digit loops
-    uint32_t run = 0;
-    for (int k = 0; k < W * DG_WARPS; k++) {
-      uint32_t t = sm_cnt[k];
-      sm_cnt[k] = run;
-      run += t;
+  if (warp == 0) {                           // exclusive scan of the W * DG_WARPS counts by one warp
+    const int total = W * DG_WARPS, per = (total + 31) / 32;
+    uint32_t sum = 0;
+    for (int k = 0; k < per; k++) {
+      int idx = lane * per + k;
+      if (idx < total) sum += sm_cnt[idx];
     }
-    sm_base = run ? atomicAdd(n_out, run) : 0u;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    uint32_t run = incl - sum;
+    for (int k = 0; k < per; k++) {
+      int idx = lane * per + k;
+      if (idx < total) {
+        uint32_t t = sm_cnt[idx];
+        sm_cnt[idx] = run;
+        run += t;
+      }
+    }
+    uint32_t block_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) sm_base = block_total ? atomicAdd(n_out, block_total) : 0u;
   }
   __syncthreads();
   const uint32_t base = sm_base;
   const uint32_t lt = (1u << lane) - 1u;
   carry = 0;
   for (int j = 0; j < W; j++) {
-    uint32_t d = signed_digit(s.v, j, c, carry, neg);
+    uint32_t d = signed_digit(sc, j, c, carry, neg);
     uint32_t b = __ballot_sync(0xffffffffu, d != 0);
     if (d) {
       uint32_t pos = base + sm_cnt[j * DG_WARPS + warp] + __popc(b & lt);

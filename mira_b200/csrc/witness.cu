@@ -93,12 +93,13 @@ __device__ __forceinline__ Fe<F> ev_fetch(uint32_t kind, uint32_t idx, const Fe<
 template <class F, int S>
 __global__ void __launch_bounds__(128) k_eval_rows(const uint4* __restrict__ prog, uint32_t n_instr, const void* __restrict__ uniforms,
                                                    const Access* __restrict__ acc, uint32_t out_kind, uint32_t out_idx,
-                                                   uint64_t row_size, void* __restrict__ out) {
+                                                   uint64_t row_size, uint64_t row_begin, uint64_t row_end,
+                                                   void* __restrict__ out) {
   extern __shared__ uint4 s_prog[];
   for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) s_prog[i] = prog[i];
   __syncthreads();
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_size; row += stride) {
+  for (uint64_t row = row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += stride) {
     Fe<F> slots[S];
     for (uint32_t pc = 0; pc < n_instr; pc++) {
       uint4 ins = s_prog[pc];
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(128) k_eval_rows(const uint4* __restrict__ pro
       slots[dst] = r;
     }
     Fe<F> res = ev_fetch<F, S>(out_kind, out_idx, slots, uniforms, acc, row, row_size);
-    fe_store<F>(reinterpret_cast<char*>(out) + row * 32, res);
+    fe_store<F>(reinterpret_cast<char*>(out) + (row - row_begin) * 32, res);
   }
 }
 
@@ -532,24 +533,26 @@ static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::ve
 }
 
 template <class F, int S>
-static int launch_eval(const uint4* prog, uint32_t n_instr, const void* uni, const Access* acc, Opnd res, uint64_t rows, void* out, cudaStream_t st) {
+static int launch_eval(const uint4* prog, uint32_t n_instr, const void* uni, const Access* acc, Opnd res, uint64_t rows, uint64_t row_begin,
+                       uint64_t row_end, void* out, cudaStream_t st) {
   size_t smem = (size_t)n_instr * 16;
   if (smem > 200 * 1024) return fail(MIRA_ERR_EVAL_PROGRAM, "program of %u device instructions does not fit shared memory", n_instr);
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_eval_rows<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_eval_rows<F, S><<<grid_for(rows, 128, 16), 128, smem, st>>>(prog, n_instr, uni, acc, res.kind, res.idx, rows, out);
+  k_eval_rows<F, S><<<grid_for(row_end - row_begin, 128, 16), 128, smem, st>>>(prog, n_instr, uni, acc, res.kind, res.idx, rows, row_begin,
+                                                                              row_end, out);
   CU(cudaGetLastError());
   return MIRA_OK;
 }
 
 template <class F>
-static int eval_impl(mira_eval_program* P, const mira_eval_domain* D, void* out, cudaStream_t st) {
+static int eval_impl(mira_eval_program* P, const mira_eval_domain* D, uint64_t row_begin, uint64_t row_end, void* out, cudaStream_t st) {
   std::vector<uint4> prog;
   std::vector<Access> access;
   Opnd res{};
   uint32_t slots = 0;
   int rc = link_program(P, D, &prog, &access, &res, &slots);
   if (rc) return rc;
-  if (!D->row_size) return MIRA_OK;
+  if (row_begin >= row_end) return MIRA_OK;
   size_t nconst = P->constants.size(), nuni = nconst + (size_t)D->num_challenges * 32 + 32;   // + the trailing ZERO
   std::vector<uint8_t> uni(nuni, 0);
   if (nconst) memcpy(uni.data(), P->constants.data(), nconst);
@@ -565,9 +568,9 @@ static int eval_impl(mira_eval_program* P, const mira_eval_domain* D, void* out,
   const uint4* dp = (const uint4*)P->d_prog.p;
   const Access* da = (const Access*)P->d_access.p;
   uint32_t ni = (uint32_t)prog.size();
-  if (slots <= 16) return launch_eval<F, 16>(dp, ni, P->d_uniforms.p, da, res, D->row_size, out, st);
-  if (slots <= 64) return launch_eval<F, 64>(dp, ni, P->d_uniforms.p, da, res, D->row_size, out, st);
-  if (slots <= 256) return launch_eval<F, 256>(dp, ni, P->d_uniforms.p, da, res, D->row_size, out, st);
+  if (slots <= 16) return launch_eval<F, 16>(dp, ni, P->d_uniforms.p, da, res, D->row_size, row_begin, row_end, out, st);
+  if (slots <= 64) return launch_eval<F, 64>(dp, ni, P->d_uniforms.p, da, res, D->row_size, row_begin, row_end, out, st);
+  if (slots <= 256) return launch_eval<F, 256>(dp, ni, P->d_uniforms.p, da, res, D->row_size, row_begin, row_end, out, st);
   return fail(MIRA_ERR_EVAL_PROGRAM, "program keeps %u intermediates live; the device interpreter supports 256", slots);
 }
 
@@ -670,8 +673,15 @@ void mira_eval_program_destroy(mira_eval_program* p) {
 }
 
 int mira_eval_rows(const mira_eval_program* prog, const mira_eval_domain* dom, void* out, int device, void* stream) {
+  if (!dom) return fail(MIRA_ERR_INVALID, "null argument");
+  return mira_eval_rows_range(prog, dom, 0, dom->row_size, out, device, stream);
+}
+
+int mira_eval_rows_range(const mira_eval_program* prog, const mira_eval_domain* dom, uint64_t row_begin, uint64_t row_end, void* out,
+                         int device, void* stream) {
   if (!prog || !dom) return fail(MIRA_ERR_INVALID, "null argument");
-  if (dom->row_size && !out) return fail(MIRA_ERR_INVALID, "null output");
+  if (row_begin > row_end || row_end > dom->row_size) return fail(MIRA_ERR_EVAL_ROW, "column variable row index out of boundary: %llu", (unsigned long long)row_end);
+  if (row_end > row_begin && !out) return fail(MIRA_ERR_INVALID, "null output");
   if ((dom->num_selectors && !dom->selectors) || (dom->num_fixed && !dom->fixed) || (dom->num_w1 && (!dom->w1 || !dom->w1_len)) ||
       (dom->num_w2 && (!dom->w2 || !dom->w2_len)) || (dom->num_challenges && !dom->challenges))
     return fail(MIRA_ERR_INVALID, "domain has a null column table");
@@ -685,8 +695,8 @@ int mira_eval_rows(const mira_eval_program* prog, const mira_eval_domain* dom, v
     cudaSetDevice(device);
   }
   p->device = device;
-  return p->field == MIRA_FQ ? eval_impl<mira::FqTag>(p, dom, out, (cudaStream_t)stream)
-                             : eval_impl<mira::FrTag>(p, dom, out, (cudaStream_t)stream);
+  return p->field == MIRA_FQ ? eval_impl<mira::FqTag>(p, dom, row_begin, row_end, out, (cudaStream_t)stream)
+                             : eval_impl<mira::FrTag>(p, dom, row_begin, row_end, out, (cudaStream_t)stream);
 }
 
 int mira_test_eval_link(const mira_eval_program* prog, const mira_eval_domain* dom, uint32_t* instr_words, size_t instr_cap,

@@ -158,15 +158,18 @@ class GraphEvaluator:
         _check(N.lib().mira_eval_program_create(field, code_arr, len(code), bytes(constants), len(constants) // ELEM, rot_arr,
                                                 len(rotations), num_intermediates, C.byref(self._h)))
 
-    def evaluate_rows(self, domain: PlonkEvalDomain, out=None, stream=None):
-        """`(0..row_size).map(|row| evaluator.evaluate(&domain, row))` (src/nifs/vanilla/mod.rs:109-116), on the GPU."""
+    def evaluate_rows(self, domain: PlonkEvalDomain, out=None, stream=None, rows=None):
+        """`(0..row_size).map(|row| evaluator.evaluate(&domain, row))` (src/nifs/vanilla/mod.rs:109-116), on the GPU.
+        rows=(begin, end) evaluates that row range only (the row-range shard of a multi-GPU run)."""
         import torch
         dev = domain.device()
+        begin, end = (0, domain.row_size) if rows is None else rows
+        count = max(end - begin, 0)
         if out is None:
-            out = torch.empty(max(domain.row_size, 1) * ELEM, dtype=torch.uint8, device=f"cuda:{dev}")
+            out = torch.empty(max(count, 1) * ELEM, dtype=torch.uint8, device=f"cuda:{dev}")
         d, keep = domain._struct()
-        _check(N.lib().mira_eval_rows(self._h, C.byref(d), out.data_ptr(), dev, _stream(stream)))
-        return out[: domain.row_size * ELEM]
+        _check(N.lib().mira_eval_rows_range(self._h, C.byref(d), begin, end, out.data_ptr(), dev, _stream(stream)))
+        return out[: count * ELEM]
 
     def stats(self) -> dict:
         st = N.EvalStats()

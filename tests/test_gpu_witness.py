@@ -309,3 +309,24 @@ def test_fft_size_limits(W):
         W.fft(FQ, a, 1)                        # no ROOT_OF_UNITY path for Fq (S = 1)
     with pytest.raises(ValueError):
         W.fft(FR, a, 2)                        # assert_eq!(n, 1 << log_n)
+
+
+def test_row_range_shards_concatenate_to_the_whole(W):
+    """Row-range sharding: ranges evaluated separately (as ranks would) concatenate to the full
+    vector, also with rotations that reach outside the range; a range past row_size is RowIndexOutOfBoundary."""
+    rng = random.Random(4)
+    rows = 1000
+    d = Domain(M, rows, 1, 2, 3, 0, 1, 2, seed=8)
+    gd = gpu_domain(W, d)
+    e = random_expr(rng, M, 1 + 2 + 6, 2, depth=6, rotations=(0, 1, -1, 17, -400))
+    p = pack_program(G.GraphEvaluator.new(e, M))
+    prog = W.GraphEvaluator(FR, p["code"], p["constants"], p["rotations"], p["num_intermediates"])
+    whole = host(prog.evaluate_rows(gd))
+    assert whole == O.eval_rows(FR, p, d.as_bytes())
+    cuts = [0, 1, 333, 334, 900, 1000]
+    parts = b"".join(host(prog.evaluate_rows(gd, rows=(a, b))) for a, b in zip(cuts, cuts[1:]))
+    assert parts == whole
+    assert prog.evaluate_rows(gd, rows=(5, 5)).numel() == 0
+    with pytest.raises(W.EvalError) as ex:
+        prog.evaluate_rows(gd, rows=(0, rows + 1))
+    assert ex.value.kind == "RowIndexOutOfBoundary"
