@@ -169,7 +169,12 @@ template <class CF>
 int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt) {
   int rc;
   const uint32_t B = plan->B;
-  const uint32_t m = B >= (1u << 14) ? 32 : (B >= 1024 ? 8 : 1);
+  // buckets per thread: the running sums are a serial chain of 2m full adds per thread, so small bucket sets get a
+  // small m (more, shorter chains: at B = 2^16 the phase was 0.7 ms of pure latency with m = 32) and only the largest
+  // sets, which have the threads to fill the machine anyway, amortise the per-thread weighting over m = 32 buckets
+  uint32_t m = B >> 15;
+  m = m < 2 ? 2 : (m > 32 ? 32 : m);
+  if (B < 2) m = 1;
   uint32_t n_red = (B + m - 1) / m;
   if ((rc = ctx->red_a.ensure((size_t)n_red * 128)) || (rc = ctx->red_b.ensure((size_t)(n_red / 128 + 2) * 128))) return rc;
   k_reduce_chunks<CF><<<(n_red + 127) / 128, 128, 0, st>>>(ctx->buckets.p, B, m, ctx->red_a.p);

@@ -17,10 +17,17 @@
 namespace mira_host {
 
 constexpr int RS_BINS = 256;
-constexpr int RS_ITEMS = 16;                       // pairs per thread
+#ifndef MIRA_RS_ITEMS
+#define MIRA_RS_ITEMS 8
+#endif
+#ifndef MIRA_RS_THREADS
+#define MIRA_RS_THREADS 512
+#endif
+constexpr int RS_ITEMS = MIRA_RS_ITEMS;            // pairs per thread
 
-// Tile geometry: THREADS x RS_ITEMS pairs per tile.  <256>: 4096-pair tiles, ~42 KB of shared memory and <= 80
-// registers, so three to four blocks are resident per SM (the 512-thread / 8192-pair variant fitted one).
+// Tile geometry: THREADS x RS_ITEMS pairs per tile.  Measured at 2^24 points (3 passes, ms): 256x16 5.61, 256x8 5.51,
+// 384x8 5.17, 512x8 4.91 (shipped), 512x4 6.02, 768x4 6.05, 1024x4 5.67, 1024x8 6.09.  ncu (profiles/r01_msm_aux_v7.txt): the scatter is
+// latency-bound (46 % of stall samples wait for the tile's own key loads), not bandwidth-bound (24 % of HBM peak).
 template <int THREADS> struct RsCfg {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int TILE = THREADS * RS_ITEMS;
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) k_radix_scatter(const uint32_t* __res
   }
 }
 
-constexpr int RS_THREADS = 256;                    // the shipped geometry
+constexpr int RS_THREADS = MIRA_RS_THREADS;        // the shipped geometry
 constexpr int RS_TILE = RsCfg<RS_THREADS>::TILE;
 
 size_t radix_sort_temp_bytes(size_t max_pairs) {
