@@ -71,6 +71,14 @@ int mira_msm_commit(mira_msm_ctx *ctx, const void *scalars, size_t n, void *out_
  * returned to the host because every caller hashes it (src/poseidon/poseidon_hash.rs:129-143). */
 int mira_msm_commit_device(mira_msm_ctx *ctx, const void *scalars_dev, size_t n, void *out_affine, void *stream);
 
+/* `cross_terms.iter().map(|v| ck.commit(v))` (src/nifs/vanilla/mod.rs:124-127) as ONE call: `count` (<= 32)
+ * device vectors of the same length n against the same key.  scalars_dev is a HOST array of device pointers;
+ * out_affine receives count x 64 B.  Each result is bit-identical to mira_msm_commit_device on that vector; the
+ * vectors share one sort, one accumulation and one reduction launch sequence, which is what makes the 2^19-row
+ * commitments of a fold step efficient.  n > len => MIRA_ERR_TOO_LONG_INPUT, nothing written. */
+int mira_msm_commit_batch(mira_msm_ctx *ctx, const void *const *scalars_dev, size_t count, size_t n, void *out_affine,
+                          void *stream);
+
 /* ---- point-range sharding --------------------------------------------------------
  * A rank that owns bases [lo, hi) creates its context over that slice and calls *_partial with the
  * matching scalar slice; the result is the un-normalised partial sum as 128 B XYZZ

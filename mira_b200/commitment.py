@@ -167,6 +167,15 @@ class CommitmentKey:
         _check(N.lib().mira_msm_commit_device(self._ctx, scalars_dev_ptr, n, out, stream or None), n, self._n)
         return out.raw
 
+    def commit_batch_device(self, scalar_dev_ptrs, n: int, stream: int = 0):
+        """`vs.iter().map(|v| ck.commit(v))` for device vectors of equal length n in one call (one sort, one
+        accumulation, one reduction for all of them).  Returns a list of 64-byte commitments."""
+        k = len(scalar_dev_ptrs)
+        ptrs = (C.c_void_p * max(k, 1))(*scalar_dev_ptrs)
+        out = C.create_string_buffer(POINT_BYTES * max(k, 1))
+        _check(N.lib().mira_msm_commit_batch(self._ctx, ptrs, k, n, out, stream or None), n, self._n)
+        return [out.raw[POINT_BYTES * i:POINT_BYTES * (i + 1)] for i in range(k)]
+
     def partial(self, scalars, n: Optional[int] = None, on_device: bool = False, stream: int = 0) -> bytes:
         """Un-normalised XYZZ partial sum (128 B) of this rank's slice."""
         if on_device:

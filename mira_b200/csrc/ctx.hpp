@@ -67,7 +67,7 @@ struct mira_msm_ctx {
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
-  void* h_result = nullptr;  // pinned, 256 B
+  void* h_result = nullptr;  // pinned, 4 KiB (up to 32 affine results of a batched commit)
   int forced_window = 0;
   size_t slice_min = (size_t)1 << 21;          // host-buffer commits are pipelined in up to 4 slices of >= this many scalars
   bool profiling = false;
@@ -80,6 +80,7 @@ namespace mira_host {
 // Per-curve entry points (curve_bn254.cu / curve_grumpkin.cu instantiate the templates in pipeline.cuh)
 struct CurveOps {
   int (*commit)(mira_msm_ctx*, const void* scalars, size_t n, int on_device, void* out, bool want_affine, cudaStream_t st);
+  int (*commit_batch)(mira_msm_ctx*, const void* const* scalar_sets_dev, size_t count, size_t n, void* out, cudaStream_t st);
   int (*prepare)(mira_msm_ctx*, size_t n);
   int (*check_on_curve)(mira_msm_ctx*);
   int (*combine)(const void* partials_host, size_t count, void* out_affine_host);

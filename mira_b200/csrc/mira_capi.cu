@@ -76,7 +76,7 @@ int mira_msm_ctx_create(int curve, const void* bases, size_t n_bases, int bases_
   ctx->n_bases = n_bases;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bases, n_bases ? n_bases * 64 : 64);
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_result, 256);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_result, 4096);
   if (e == cudaSuccess && n_bases)
     e = cudaMemcpyAsync(ctx->d_bases, bases, n_bases * 64, bases_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -133,6 +133,20 @@ int mira_msm_commit_device(mira_msm_ctx* ctx, const void* scalars_dev, size_t n,
 }
 int mira_msm_partial(mira_msm_ctx* ctx, const void* scalars, size_t n, int scalars_on_device, void* out_xyzz, void* stream) {
   return dispatch_commit(ctx, scalars, n, scalars_on_device, out_xyzz, false, stream);
+}
+
+int mira_msm_commit_batch(mira_msm_ctx* ctx, const void* const* scalars_dev, size_t count, size_t n, void* out_affine, void* stream) {
+  if (!ctx || (count && (!scalars_dev || !out_affine))) return fail(MIRA_ERR_INVALID, "null argument");
+  if (count > 32) return fail(MIRA_ERR_INVALID, "at most 32 vectors per batched commit");
+  if (n > ctx->n_bases)
+    return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
+  for (size_t k = 0; k < count; k++)
+    if (n && !scalars_dev[k]) return fail(MIRA_ERR_INVALID, "vector %zu is null", k);
+  if (!count) return MIRA_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return ops_for(ctx->curve).commit_batch(ctx, scalars_dev, count, n, out_affine, st);
 }
 
 int mira_msm_combine(int curve, const void* partials, size_t count, int device, void* out_affine) {

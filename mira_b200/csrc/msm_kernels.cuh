@@ -52,8 +52,10 @@ __device__ __forceinline__ uint32_t signed_digit(const uint32_t* sc, int j, int 
 
 template <class SF>
 __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ scalars, uint32_t n, uint32_t first, int c, int W,
-                                                       uint32_t n_cover, uint32_t* __restrict__ keys,
+                                                       uint32_t n_cover, uint32_t key_offset, uint32_t* __restrict__ keys,
                                                        uint32_t* __restrict__ refs, uint32_t* __restrict__ n_out) {
+  // key_offset: batched commits (several scalar vectors against the same key) give every vector its own bucket set;
+  // the pairs of all vectors then go through ONE sort and ONE accumulation
   extern __shared__ uint32_t sm_cnt[];       // [W][DG_WARPS] pair counts -> exclusive offsets
   __shared__ uint32_t sm_sc[DG_THREADS * 9];
   __shared__ uint32_t sm_base;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ 
     uint32_t b = __ballot_sync(0xffffffffu, d != 0);
     if (d) {
       uint32_t pos = base + sm_cnt[j * DG_WARPS + warp] + __popc(b & lt);
-      keys[pos] = d;
+      keys[pos] = key_offset + d;
       refs[pos] = ((uint32_t)j * n_cover + first + i) | neg;     // `scalars` is the slice starting at key index `first`
     }
   }
@@ -295,8 +297,11 @@ __global__ void __launch_bounds__(HV_THREADS) k_combine_heavy(const uint32_t* __
 // ------------------------------------------------------------------ bucket reduction
 // buckets[1..B]; thread t owns b in [t*m+1, (t+1)*m]:  out[t] = sum (b - t*m) * bucket[b] + (t*m) * sum bucket[b]
 template <class CF>
-__global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets, uint32_t B, uint32_t m,
-                                                       void* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ buckets_all, uint32_t B, uint32_t m,
+                                                       void* __restrict__ out_all, size_t in_stride, size_t out_stride) {
+  // blockIdx.y selects the bucket set of a batched commit (strides in bytes)
+  const void* buckets = reinterpret_cast<const char*>(buckets_all) + blockIdx.y * in_stride;
+  void* out = reinterpret_cast<char*>(out_all) + blockIdx.y * out_stride;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t lo = t * m;
   if (lo >= B) return;
@@ -316,9 +321,11 @@ __global__ void __launch_bounds__(128) k_reduce_chunks(const void* __restrict__ 
 
 // Sum `n` XYZZ points into ceil(n / per_block) points: each block sums a contiguous slice.
 template <class CF>
-__global__ void __launch_bounds__(128) k_sum_points(const void* __restrict__ in, uint32_t n, uint32_t per_thread,
-                                                    void* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_sum_points(const void* __restrict__ in_all, uint32_t n, uint32_t per_thread,
+                                                    void* __restrict__ out_all, size_t in_stride = 0, size_t out_stride = 0) {
   __shared__ uint4 sm[128 * 8];   // 128 XYZZ points
+  const void* in = reinterpret_cast<const char*>(in_all) + blockIdx.y * in_stride;
+  void* out = reinterpret_cast<char*>(out_all) + blockIdx.y * out_stride;
   uint32_t per_block = per_thread * blockDim.x;
   uint32_t base = blockIdx.x * per_block + threadIdx.x * per_thread;
   Xyzz<CF> acc = xyzz_identity<CF>();
@@ -345,9 +352,9 @@ __global__ void __launch_bounds__(128) k_sum_points(const void* __restrict__ in,
 
 template <class CF>
 __global__ void k_finalize(const void* __restrict__ in_xyzz, void* __restrict__ out_affine) {
-  if (threadIdx.x || blockIdx.x) return;
-  Xyzz<CF> p = xyzz_load<CF>(in_xyzz);
-  aff_store<CF>(out_affine, xyzz_to_affine(p));
+  if (threadIdx.x) return;       // one block per point (a batched commit normalises all its results in one launch)
+  Xyzz<CF> p = xyzz_load<CF>(reinterpret_cast<const char*>(in_xyzz) + (size_t)blockIdx.x * 128);
+  aff_store<CF>(reinterpret_cast<char*>(out_affine) + (size_t)blockIdx.x * 64, xyzz_to_affine(p));
 }
 
 // ------------------------------------------------------------------ fixed-base table

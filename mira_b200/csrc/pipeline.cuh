@@ -84,55 +84,65 @@ struct PhaseTimer {
 //   msm_begin   picks the window, fetches the fixed-base table, sizes the workspace, clears the buckets
 //   msm_slice   digits -> sort -> accumulate for scalars [first, first + n_slice); add_mode folds into the buckets
 //   msm_finish  bucket reduction; leaves the XYZZ sum (128 B) in ctx->result.p
+constexpr int MAX_BATCH = 32;
 struct MsmPlan {
   int c = 0, W = 0;
   Table* tab = nullptr;
   uint32_t B = 0;
+  int n_sets = 1;           // bucket sets (scalar vectors committed together against the same key)
   size_t max_slice = 0;
   uint64_t launches = 0;
   uint64_t entries = 0;
 };
 
 template <class CF>
-int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan) {
+int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan, int n_sets = 1) {
   int rc;
   int c = ctx->forced_window ? ctx->forced_window : choose_window(n);
   Table* tab = nullptr;
   if ((rc = get_table<CF>(ctx, c, n, &tab))) return rc;
   const int W = tab->W;
-  const size_t E = max_slice * (size_t)W;
-  if (n * (size_t)W >= (size_t)0x7fffffff || (size_t)W * tab->n_cover >= (size_t)0x7fffffff)
-    return fail(MIRA_ERR_INVALID, "commit of %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it", n, n * (size_t)W);
+  const size_t E = max_slice * (size_t)W * (size_t)n_sets;
   const uint32_t B = 1u << (c - 1);
+  if (n * (size_t)W * (size_t)n_sets >= (size_t)0x7fffffff || (size_t)W * tab->n_cover >= (size_t)0x7fffffff ||
+      ((size_t)B + 1) * (size_t)n_sets >= (size_t)PK_KEY_MASK)
+    return fail(MIRA_ERR_INVALID, "commit of %d x %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it",
+                n_sets, n, n * (size_t)W * (size_t)n_sets);
+  const size_t bucket_bytes = ((size_t)B + 1) * 128 * (size_t)n_sets;
   if ((rc = ctx->keys.ensure(E * 4 + 16)) || (rc = ctx->refs.ensure(E * 4 + 16)) || (rc = ctx->skeys.ensure(E * 4 + 16)) ||
-      (rc = ctx->srefs.ensure(E * 4 + 16)) || (rc = ctx->counts.ensure(64)) || (rc = ctx->buckets.ensure(((size_t)B + 1) * 128)) ||
+      (rc = ctx->srefs.ensure(E * 4 + 16)) || (rc = ctx->counts.ensure(64)) || (rc = ctx->buckets.ensure(bucket_bytes)) ||
       (rc = ctx->tile_sums.ensure(radix_sort_temp_bytes(E))))
     return rc;
-  CU(cudaMemsetAsync(ctx->buckets.p, 0, ((size_t)B + 1) * 128, st));
-  plan->c = c; plan->W = W; plan->tab = tab; plan->B = B; plan->max_slice = max_slice;
+  CU(cudaMemsetAsync(ctx->buckets.p, 0, bucket_bytes, st));
+  plan->c = c; plan->W = W; plan->tab = tab; plan->B = B; plan->max_slice = max_slice; plan->n_sets = n_sets;
   plan->launches = 0; plan->entries = 0;
   return MIRA_OK;
 }
 
 template <class CF, class SF>
-int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, size_t first, size_t n, bool add_mode, cudaStream_t st,
-              PhaseTimer* pt) {
+int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets, size_t first, size_t n, bool add_mode,
+              cudaStream_t st, PhaseTimer* pt) {
   int rc;
   const int c = plan->c, W = plan->W;
   Table* tab = plan->tab;
-  const size_t E = n * (size_t)W;
+  const size_t E = n * (size_t)W * (size_t)plan->n_sets;
   uint32_t* d_npairs = (uint32_t*)ctx->counts.p;     // number of (bucket, ref) pairs, produced on the device
   if (pt) pt->mark(0);
   // ---- digits (compacted pair list)
   CU(cudaMemsetAsync(d_npairs, 0, 4, st));
-  k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
-      d_scalars, (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, d_npairs);
-  plan->launches++;
+  for (int s = 0; s < plan->n_sets; s++) {
+    k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
+        d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), (uint32_t*)ctx->keys.p,
+        (uint32_t*)ctx->refs.p, d_npairs);
+    plan->launches++;
+  }
   if (pt) pt->mark(1);
   // ---- group pairs by bucket: LSD radix sort on the c-bit key
   int in_b = 0;
-  if ((rc = radix_sort_pairs((uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p, d_npairs, E, c,
-                             ctx->tile_sums.p, st, &in_b, &plan->launches)))
+  int key_bits = c;          // keys are < n_sets * (B + 1)
+  while (((uint64_t)1 << key_bits) < (uint64_t)plan->n_sets * (plan->B + 1)) key_bits++;
+  if ((rc = radix_sort_pairs((uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p, d_npairs, E,
+                             key_bits, ctx->tile_sums.p, st, &in_b, &plan->launches)))
     return rc;
   const uint32_t* skeys = (const uint32_t*)(in_b ? ctx->skeys.p : ctx->keys.p);
   const uint32_t* srefs = (const uint32_t*)(in_b ? ctx->srefs.p : ctx->refs.p);
@@ -169,6 +179,7 @@ template <class CF>
 int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt) {
   int rc;
   const uint32_t B = plan->B;
+  const unsigned S = (unsigned)plan->n_sets;
   // buckets per thread: the running sums are a serial chain of 2m full adds per thread, so small bucket sets get a
   // small m (more, shorter chains: at B = 2^16 the phase was 0.7 ms of pure latency with m = 32) and only the largest
   // sets, which have the threads to fill the machine anyway, amortise the per-thread weighting over m = 32 buckets
@@ -176,22 +187,27 @@ int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt
   m = m < 2 ? 2 : (m > 32 ? 32 : m);
   if (B < 2) m = 1;
   uint32_t n_red = (B + m - 1) / m;
-  if ((rc = ctx->red_a.ensure((size_t)n_red * 128)) || (rc = ctx->red_b.ensure((size_t)(n_red / 128 + 2) * 128))) return rc;
-  k_reduce_chunks<CF><<<(n_red + 127) / 128, 128, 0, st>>>(ctx->buckets.p, B, m, ctx->red_a.p);
+  const size_t a_stride = (size_t)n_red * 128, b_stride = (size_t)(n_red / 128 + 2) * 128;
+  if ((rc = ctx->red_a.ensure(a_stride * S)) || (rc = ctx->red_b.ensure(b_stride * S)) || (rc = ctx->result.ensure((size_t)S * 192 + 256)))
+    return rc;
+  k_reduce_chunks<CF><<<dim3((n_red + 127) / 128, S), 128, 0, st>>>(ctx->buckets.p, B, m, ctx->red_a.p, ((size_t)B + 1) * 128, a_stride);
   plan->launches++;
   void* src = ctx->red_a.p;
   void* dst = ctx->red_b.p;
+  size_t src_stride = a_stride, dst_stride = b_stride;
   uint32_t cnt = n_red;
   while (cnt > 1) {
     uint32_t per_thread = cnt > 128 * 8 ? 8 : 1;
     uint32_t per_block = per_thread * 128;
     uint32_t blocks = (cnt + per_block - 1) / per_block;
-    k_sum_points<CF><<<blocks, 128, 0, st>>>(src, cnt, per_thread, dst);
+    k_sum_points<CF><<<dim3(blocks, S), 128, 0, st>>>(src, cnt, per_thread, dst, src_stride, dst_stride);
     plan->launches++;
     cnt = blocks;
     std::swap(src, dst);
+    std::swap(src_stride, dst_stride);
   }
-  CU(cudaMemcpyAsync(ctx->result.p, src, 128, cudaMemcpyDeviceToDevice, st));
+  // result.p: S x 128 B XYZZ sums, followed (at S * 128) by S x 64 B for the affine results
+  CU(cudaMemcpy2DAsync(ctx->result.p, 128, src, src_stride, 128, S, cudaMemcpyDeviceToDevice, st));
   if (pt) pt->mark(4);
   CU(cudaGetLastError());
   ctx->stats.window_bits = plan->c;
@@ -215,7 +231,8 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
   MsmPlan plan;
   PhaseTimer pt(ctx->profiling, st);
   if ((rc = msm_begin<CF>(ctx, n, n, st, &plan))) return rc;
-  if ((rc = msm_slice<CF, SF>(ctx, &plan, d_scalars, 0, n, false, st, &pt))) return rc;
+  const void* sets[1] = {d_scalars};
+  if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, 0, n, false, st, &pt))) return rc;
   if ((rc = msm_finish<CF>(ctx, &plan, st, &pt))) return rc;
   if (ctx->profiling) {
     CU(cudaStreamSynchronize(st));
@@ -266,7 +283,8 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   for (size_t first = 0; first < n; first += per, k++) {
     size_t cnt = n - first < per ? n - first : per;
     CU(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
-    if ((rc = msm_slice<CF, SF>(ctx, &plan, (const char*)ctx->scalars.p + first * 32, first, cnt, k > 0, st, nullptr))) return rc;
+    const void* sets[1] = {(const char*)ctx->scalars.p + first * 32};
+    if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, first, cnt, k > 0, st, nullptr))) return rc;
   }
   return msm_finish<CF>(ctx, &plan, st, nullptr);
 }
@@ -291,6 +309,31 @@ int commit_impl(mira_msm_ctx* ctx, const void* scalars, size_t n, int on_device,
   return MIRA_OK;
 }
 
+
+// Several vectors of the same length against the same key (the 5-6 cross-term commitments of one fold,
+// src/nifs/vanilla/mod.rs:124-127): one digit kernel per vector, then ONE sort, accumulation and reduction over
+// `count` bucket sets, one normalisation launch, one D2H of count x 64 B.
+template <class CF, class SF>
+int commit_batch_impl(mira_msm_ctx* ctx, const void* const* d_scalar_sets, size_t count, size_t n, void* out, cudaStream_t st) {
+  int rc;
+  if ((rc = ctx->result.ensure(count * 192 + 256))) return rc;
+  if (n == 0) {
+    memset(out, 0, count * 64);
+    ctx->stats = mira_msm_stats{};
+    return MIRA_OK;
+  }
+  MsmPlan plan;
+  if ((rc = msm_begin<CF>(ctx, n, n, st, &plan, (int)count))) return rc;
+  if ((rc = msm_slice<CF, SF>(ctx, &plan, d_scalar_sets, 0, n, false, st, nullptr))) return rc;
+  if ((rc = msm_finish<CF>(ctx, &plan, st, nullptr))) return rc;
+  char* aff = (char*)ctx->result.p + count * 128;
+  k_finalize<CF><<<(unsigned)count, 32, 0, st>>>(ctx->result.p, aff);
+  ctx->stats.kernel_launches++;
+  CU(cudaMemcpyAsync(ctx->h_result, aff, count * 64, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(out, ctx->h_result, count * 64);
+  return MIRA_OK;
+}
 
 template <class CF>
 int prepare_impl(mira_msm_ctx* ctx, size_t n) {

@@ -290,3 +290,32 @@ def test_sliced_host_commit_equals_unsliced(gpu, curve, dist):
     ck = CommitmentKey(curve, bases)
     ck.set_slice_min(5000)
     assert ck.commit(one) == O.commit(curve, bases, one)
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_batched_commit_equals_individual_commits(gpu, curve):
+    """mira_msm_commit_batch == `vs.iter().map(|v| ck.commit(v))` (src/nifs/vanilla/mod.rs:124-127), bit for bit:
+    the vectors share one sort / accumulation / reduction but each keeps its own bucket set."""
+    from mira_b200 import CommitmentKey, TooLongInput
+    n = 5000
+    bases = O.gen_bases(curve, 31, n)
+    ck = CommitmentKey(curve, bases)
+    vecs = [O.gen_scalars(curve, 40 + k, n, k % 2) for k in range(6)]
+    vecs[3] = bytes(32 * n)                                        # an all-zero cross term (the `None` arm, :118)
+    vecs[4] = O.gen_scalars(curve, 5, 1, 0) * n                    # one heavy bucket per window
+    want = [O.commit(curve, bases, v) for v in vecs]
+    assert want[3] == bytes(64)
+    devs = [torch.frombuffer(bytearray(v), dtype=torch.uint8).cuda() for v in vecs]
+    for c in (0, 7, 12):
+        ck.set_window(c)
+        for count in (1, 2, 6):
+            got = ck.commit_batch_device([d.data_ptr() for d in devs[:count]], n)
+            assert got == want[:count]
+    ck.set_window(0)
+    assert ck.commit_batch_device([], n) == []
+    m = 1237                                                       # prefix of the key, ragged length
+    got = ck.commit_batch_device([d.data_ptr() for d in devs[:3]], m)
+    assert got == [O.commit(curve, bases[:64 * m], v[:32 * m]) for v in vecs[:3]]
+    with pytest.raises(TooLongInput):
+        ck.commit_batch_device([devs[0].data_ptr()], n + 1)
+    assert ck.commit(vecs[0]) == want[0]                           # the single-vector path still works afterwards

@@ -53,8 +53,9 @@ def points_per_step(sh) -> int:
 
 # ------------------------------------------------------------------------------------------ GPU arm
 class GpuFoldStep:
-    def __init__(self, log_rows: int, device: int = 0):
+    def __init__(self, log_rows: int, device: int = 0, batch: bool = True):
         import torch
+        self.batch = batch
         import gpu_util
         from mira_b200 import CommitmentKey
         from mira_b200 import witness as W
@@ -101,7 +102,10 @@ class GpuFoldStep:
                 dom = W.PlonkEvalDomain(s["meta"]["num_advice"], 0, st["ch"], [], st["fixed"], [st["W1"]], [st["W2"]])
                 for prog, t in zip(st["progs"], st["T"]):
                     prog.evaluate_rows(dom, out=t, stream=sh)
-                    commits.append(ck.commit_device(t.data_ptr(), s["rows"], sh))
+                if self.batch:      # all cross-term commitments of the fold in one call
+                    commits += ck.commit_batch_device([t.data_ptr() for t in st["T"]], s["rows"], sh)
+                else:
+                    commits += [ck.commit_device(t.data_ptr(), s["rows"], sh) for t in st["T"]]
                 W.fold_w(s["field"], st["W1"], st["W2"], st["r"], out=st["W_out"], stream=sh)
                 W.fold_e(s["field"], st["E"], st["T"], st["r"], out=st["E_out"], stream=sh)
         return commits
