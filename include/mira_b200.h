@@ -181,7 +181,7 @@ typedef struct {
   uint32_t uniforms;       /* constants + challenges */
   uint32_t muls, adds;     /* field multiplications (incl. squarings) / additive ops per row */
   uint32_t loads;          /* column loads executed per row */
-  uint32_t _pad;
+  uint32_t fused;          /* a*b +- c*d pairs executed as one dual-product instruction (counted in muls/adds too) */
 } mira_eval_stats;
 /* statistics of the last mira_eval_rows binding of this program */
 int mira_eval_program_stats(const mira_eval_program *prog, mira_eval_stats *out);

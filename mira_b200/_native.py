@@ -45,7 +45,7 @@ class EvalDomain(C.Structure):
 
 class EvalStats(C.Structure):
     _fields_ = [("instructions", C.c_uint32), ("slots", C.c_uint32), ("accesses", C.c_uint32), ("uniforms", C.c_uint32),
-                ("muls", C.c_uint32), ("adds", C.c_uint32), ("loads", C.c_uint32), ("_pad", C.c_uint32)]
+                ("muls", C.c_uint32), ("adds", C.c_uint32), ("loads", C.c_uint32), ("fused", C.c_uint32)]
 
 
 

@@ -171,6 +171,19 @@ template <class F> __device__ __forceinline__ Fe<F> fe_sqr(const Fe<F>& a) {
   return fe_redc(fe_sqr_wide(a));
 #endif
 }
+// a*b + c*d with ONE reduction
+template <class F> __device__ __forceinline__ Fe<F> fe_mul_add_mul(const Fe<F>& a, const Fe<F>& b, const Fe<F>& c, const Fe<F>& d) {
+#if MIRA_MUL_IMPL == 0 && MIRA_DUAL_MUL
+  uint32_t bcd[24];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { bcd[i] = b.v[i]; bcd[8 + i] = c.v[i]; bcd[16 + i] = d.v[i]; }
+  Fe<F> r;
+  mont_mul2_raw(F{}, r.v, a.v, bcd);
+  return r;
+#else
+  return fe_add(fe_mul(a, b), fe_mul(c, d));
+#endif
+}
 // a*b - c*d with ONE reduction when lazy subtraction is enabled
 template <class F> __device__ __forceinline__ Fe<F> fe_mul_sub_mul(const Fe<F>& a, const Fe<F>& b, const Fe<F>& c, const Fe<F>& d) {
 #if MIRA_MUL_IMPL != 0 && MIRA_LAZY_SUB

@@ -10,6 +10,7 @@
 //   best_fft / fft / ifft                           src/fft.rs:12-27,51-115,160-175
 // Outputs stay in HBM so they feed mira_msm_commit_device without crossing PCIe.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 
 #include "ctx.hpp"
@@ -63,8 +64,9 @@ __global__ void __launch_bounds__(256) k_fold_e(const void* __restrict__ e, Fold
 }
 
 // ------------------------------------------------------------------ row evaluator
-// Device instruction (16 B): x = op | akind << 4 | bkind << 8 | dst << 16, y = a, z = b.
-enum : uint32_t { DOP_ADD = 0, DOP_SUB, DOP_MUL, DOP_SQUARE, DOP_DOUBLE, DOP_NEGATE, DOP_COPY };
+// Device instruction (16 B): x = op | akind << 4 | bkind << 8 | dst << 16, y = a, z = b,
+// w = c | ckind << 14 | d << 16 | dkind << 30 for the fused sum / difference of two products a*b +- c*d.
+enum : uint32_t { DOP_ADD = 0, DOP_SUB, DOP_MUL, DOP_SQUARE, DOP_DOUBLE, DOP_NEGATE, DOP_COPY, DOP_MUL2ADD, DOP_MUL2SUB };
 enum : uint32_t { DK_SLOT = 0, DK_UNIFORM = 1, DK_ACCESS = 2 };
 struct Access {          // one distinct (column, rotation) load
   const void* ptr;       // column base (32 B elements, or 1 B selectors)
@@ -111,6 +113,11 @@ __global__ void __launch_bounds__(128) k_eval_rows(const uint4* __restrict__ pro
         if (op == DOP_MUL) r = fe_mul(a, b);
         else if (op == DOP_ADD) r = fe_add(a, b);
         else r = fe_sub(a, b);
+      } else if (op >= DOP_MUL2ADD) {        // a*b +- c*d under ONE Montgomery reduction (field.cuh: mont_mul2)
+        Fe<F> b = ev_fetch<F, S>(bk, ins.z, slots, uniforms, acc, row, row_size);
+        Fe<F> c = ev_fetch<F, S>((ins.w >> 14) & 3u, ins.w & 0x3fffu, slots, uniforms, acc, row, row_size);
+        Fe<F> d = ev_fetch<F, S>(ins.w >> 30, (ins.w >> 16) & 0x3fffu, slots, uniforms, acc, row, row_size);
+        r = op == DOP_MUL2ADD ? fe_mul_add_mul(a, b, c, d) : fe_mul_sub_mul(a, b, c, d);
       } else if (op == DOP_SQUARE) r = fe_sqr(a);
       else if (op == DOP_DOUBLE) r = fe_dbl(a);
       else if (op == DOP_NEGATE) r = fe_neg(a);
@@ -287,6 +294,8 @@ struct LInstr {
   uint32_t op;
   int32_t dst_var;      // variable (intermediate id) defined
   Opnd a, b;
+  Opnd c{DK_UNIFORM, 0}, d{DK_UNIFORM, 0};   // only DOP_MUL2ADD / DOP_MUL2SUB
+  bool fused() const { return op == DOP_MUL2ADD || op == DOP_MUL2SUB; }
 };
 
 struct Linker {
@@ -376,6 +385,12 @@ struct Linker {
   }
 };
 
+// MIRA_EVAL_FUSE=0 disables the product-pair fusion (A/B timing and the linker tests exercise both forms)
+static bool ctx_fuse_enabled() {
+  const char* e = getenv("MIRA_EVAL_FUSE");
+  return !(e && e[0] == '0');
+}
+
 static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::vector<uint4>* out_prog, std::vector<Access>* out_access,
                         Opnd* out_result, uint32_t* out_slots) {
   Linker L(*P, *D);
@@ -464,10 +479,49 @@ static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::ve
   Opnd result = zero_uniform;
   bool have_result = last_target >= 0;
   if (have_result) result = aliased[last_target] ? alias[last_target] : Opnd{DK_SLOT, (uint32_t)last_target};
+  // pass 2b: fuse  t1 = a*b; t2 = c*d; r = t1 +- t2  (t1, t2 read nowhere else) into ONE instruction that forms
+  // both products under a single Montgomery reduction: 200 wide MACs instead of 272 and two slot round trips fewer.
+  // Exact arithmetic makes this value-preserving.  Only for programs whose targets are unique (what
+  // GraphEvaluator::add_calculation produces): then no operand can change between the product and the sum.
+  P->stats.fused = 0;
+  if (ssa && ctx_fuse_enabled()) {
+    std::vector<int> uses(NV, 0), def(NV, -1);
+    auto count_use = [&](const Opnd& o) { if (o.kind == DK_SLOT) uses[o.idx]++; };
+    for (size_t i = 0; i < ins.size(); i++) {
+      def[ins[i].dst_var] = (int)i;
+      count_use(ins[i].a);
+      if (ins[i].op <= DOP_MUL) count_use(ins[i].b);
+    }
+    if (have_result && result.kind == DK_SLOT) uses[result.idx]++;
+    auto product_of = [&](const Opnd& o, Opnd* x, Opnd* y) -> bool {
+      if (o.kind != DK_SLOT || uses[o.idx] != 1 || def[o.idx] < 0) return false;
+      const LInstr& M = ins[def[o.idx]];
+      if (M.op == DOP_MUL) { *x = M.a; *y = M.b; return true; }
+      if (M.op == DOP_SQUARE) { *x = M.a; *y = M.a; return true; }
+      return false;
+    };
+    auto fits = [](const Opnd& o) { return o.idx < 0x4000u; };
+    for (size_t i = 0; i < ins.size(); i++) {
+      LInstr& I = ins[i];
+      if (I.op != DOP_ADD && I.op != DOP_SUB) continue;
+      if (I.a.kind == DK_SLOT && I.b.kind == DK_SLOT && I.a.idx == I.b.idx) continue;
+      Opnd a1, a2, b1, b2;
+      if (!product_of(I.a, &a1, &a2) || !product_of(I.b, &b1, &b2) || !fits(b1) || !fits(b2)) continue;
+      I.op = I.op == DOP_ADD ? DOP_MUL2ADD : DOP_MUL2SUB;
+      I.a = a1; I.b = a2; I.c = b1; I.d = b2;       // the two MUL/SQUARE instructions become dead code below
+      P->stats.fused++;
+    }
+  }
   // pass 3: liveness (last read of every variable), dead-code removal, slot allocation
   const int NI = (int)ins.size();
   std::vector<int> last_use(NV, -1);
   std::vector<char> live(NI, 0);
+  auto operands_of = [](const LInstr& I, Opnd* o) -> int {
+    o[0] = I.a;
+    if (I.fused()) { o[1] = I.b; o[2] = I.c; o[3] = I.d; return 4; }
+    if (I.op <= DOP_MUL) { o[1] = I.b; return 2; }
+    return 1;
+  };
   {
     std::vector<char> needed(NV, 0);
     if (have_result && result.kind == DK_SLOT) needed[result.idx] = 1;
@@ -475,16 +529,21 @@ static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::ve
       LInstr& I = ins[i];
       if (!needed[I.dst_var]) continue;
       live[i] = 1;
-      bool self = (I.a.kind == DK_SLOT && (int32_t)I.a.idx == I.dst_var) || (I.b.kind == DK_SLOT && (int32_t)I.b.idx == I.dst_var);
+      Opnd o[4];
+      int no = operands_of(I, o);
+      bool self = false;
+      for (int k = 0; k < no; k++) self = self || (o[k].kind == DK_SLOT && (int32_t)o[k].idx == I.dst_var);
       if (!self) needed[I.dst_var] = 0;
-      if (I.a.kind == DK_SLOT) needed[I.a.idx] = 1;
-      if (I.b.kind == DK_SLOT) needed[I.b.idx] = 1;
+      for (int k = 0; k < no; k++)
+        if (o[k].kind == DK_SLOT) needed[o[k].idx] = 1;
     }
   }
   for (int i = 0; i < NI; i++) {
     if (!live[i]) continue;
-    if (ins[i].a.kind == DK_SLOT) last_use[ins[i].a.idx] = i;
-    if (ins[i].b.kind == DK_SLOT) last_use[ins[i].b.idx] = i;
+    Opnd o[4];
+    int no = operands_of(ins[i], o);
+    for (int k = 0; k < no; k++)
+      if (o[k].kind == DK_SLOT) last_use[o[k].idx] = i;
   }
   if (have_result && result.kind == DK_SLOT) last_use[result.idx] = NI;
   std::vector<int32_t> slot_of(NV, -1);
@@ -498,13 +557,18 @@ static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::ve
       if (o.kind != DK_SLOT) return o;
       return slot_of[o.idx] >= 0 ? Opnd{DK_SLOT, (uint32_t)slot_of[o.idx]} : zero_uniform;
     };
-    Opnd a = map_op(I.a), b = map_op(I.b);
+    Opnd src[4], mapped[4];
+    int no = operands_of(I, src);
+    for (int k = 0; k < no; k++) mapped[k] = map_op(src[k]);
+    for (int k = no; k < 4; k++) mapped[k] = mapped[0];
     // operands whose last read is this instruction release their slot before the destination is chosen
-    for (Opnd o : {I.a, I.b})
+    for (int k = 0; k < no; k++) {
+      const Opnd& o = src[k];
       if (o.kind == DK_SLOT && last_use[o.idx] == i && (int32_t)o.idx != I.dst_var && slot_of[o.idx] >= 0) {
         free_slots.push_back((uint32_t)slot_of[o.idx]);
         slot_of[o.idx] = -1;
       }
+    }
     if (slot_of[I.dst_var] < 0) {
       if (!free_slots.empty()) {
         slot_of[I.dst_var] = (int32_t)free_slots.back();
@@ -515,10 +579,17 @@ static int link_program(mira_eval_program* P, const mira_eval_domain* D, std::ve
     }
     uint32_t dst = (uint32_t)slot_of[I.dst_var];
     if (dst > 0xffff) return fail(MIRA_ERR_EVAL_PROGRAM, "program needs more than 65535 live intermediates");
-    out_prog->push_back(make_uint4(I.op | (a.kind << 4) | (b.kind << 8) | (dst << 16), a.idx, b.idx, 0));
-    if (I.op == DOP_MUL || I.op == DOP_SQUARE) P->stats.muls++;
+    const Opnd &a = mapped[0], &b = mapped[1];
+    uint32_t w = 0;
+    if (I.fused()) {
+      if (mapped[2].idx >= 0x4000u || mapped[3].idx >= 0x4000u) return fail(MIRA_ERR_EVAL_PROGRAM, "fused operand index out of range");
+      w = mapped[2].idx | (mapped[2].kind << 14) | (mapped[3].idx << 16) | (mapped[3].kind << 30);
+    }
+    out_prog->push_back(make_uint4(I.op | (a.kind << 4) | (b.kind << 8) | (dst << 16), a.idx, b.idx, w));
+    if (I.fused()) { P->stats.muls += 2; P->stats.adds++; }
+    else if (I.op == DOP_MUL || I.op == DOP_SQUARE) P->stats.muls++;
     else if (I.op != DOP_COPY) P->stats.adds++;
-    P->stats.loads += (a.kind == DK_ACCESS) + (I.op <= DOP_MUL && b.kind == DK_ACCESS);
+    for (int k = 0; k < no; k++) P->stats.loads += mapped[k].kind == DK_ACCESS;
   }
   if (have_result && result.kind == DK_SLOT) result = slot_of[result.idx] >= 0 ? Opnd{DK_SLOT, (uint32_t)slot_of[result.idx]} : zero_uniform;
   if (result.kind == DK_ACCESS) P->stats.loads++;

@@ -82,11 +82,16 @@ def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
     for row in range(rows):
         slots = [None] * max(ns.value, 1)
         for k in range(ni.value):
-            w0, a, b = iw[4 * k], iw[4 * k + 1], iw[4 * k + 2]
+            w0, a, b, w3 = iw[4 * k], iw[4 * k + 1], iw[4 * k + 2], iw[4 * k + 3]
             op, ak, bk, dst = w0 & 0xf, (w0 >> 4) & 0xf, (w0 >> 8) & 0xf, w0 >> 16
             assert dst < ns.value
             x = fetch(ak, a, slots, row)
-            if op <= 2:
+            if op >= 7:                                  # fused a*b +- c*d
+                y = fetch(bk, b, slots, row)
+                c = fetch((w3 >> 14) & 3, w3 & 0x3fff, slots, row)
+                d = fetch(w3 >> 30, (w3 >> 16) & 0x3fff, slots, row)
+                v = x * y + c * d if op == 7 else x * y - c * d
+            elif op <= 2:
                 y = fetch(bk, b, slots, row)
                 v = (x + y) if op == 0 else (x - y) if op == 1 else x * y
             elif op == 3: v = x * x
@@ -95,7 +100,8 @@ def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
             else: v = x
             slots[dst] = v % M
         out.append(fetch(rk.value, ri.value, slots, row))
-    return 0, out, {"instructions": ni.value, "slots": ns.value, "accesses": na.value, "muls": st.muls, "adds": st.adds, "loads": st.loads}
+    return 0, out, {"instructions": ni.value, "slots": ns.value, "accesses": na.value, "muls": st.muls, "adds": st.adds, "loads": st.loads,
+                    "fused": st.fused}
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -121,8 +127,27 @@ def test_linked_cross_term_programs(T, n_gates, max_slots):
         assert out == unmont(O.eval_rows(R.FR, pack_program(p), d.as_bytes()), M)
         c = p.counts()
         assert st["muls"] == c["mul"] and st["adds"] == c["add"]        # nothing but Stores is removed
-        assert st["instructions"] == c["mul"] + c["add"]
+        assert st["instructions"] == c["mul"] + c["add"] - 2 * st["fused"]
+        assert st["fused"] > 0.2 * c["add"]                                # the sum-of-two-products fusion fires
         assert st["slots"] <= max_slots, st
+
+
+def test_fusion_can_be_disabled_and_gives_the_same_values(monkeypatch):
+    progs, meta = G.cross_term_programs(5, 1, M)
+    d = Domain(M, 3, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=56, sparse=True)
+    rc, fused_out, st1 = link_and_simulate(progs[1], d)
+    monkeypatch.setenv("MIRA_EVAL_FUSE", "0")
+    rc2, plain_out, st0 = link_and_simulate(progs[1], d)
+    assert rc == rc2 == 0 and fused_out == plain_out
+    assert st0["fused"] == 0 and st1["fused"] > 0 and st1["instructions"] == st0["instructions"] - 2 * st1["fused"]
+    # a - b with both products: difference of two squares, and an ADD of the same product twice is left alone
+    e = (G.Polynomial(meta["num_fixed"]) * G.Polynomial(meta["num_fixed"])) - (G.Polynomial(1) * G.Polynomial(1))
+    monkeypatch.delenv("MIRA_EVAL_FUSE")
+    rc, out, st = link_and_simulate(G.GraphEvaluator.new(e, M), d)
+    assert rc == 0 and st["fused"] == 1 and st["instructions"] == 1 and out == d.direct(e, range(3))
+    x = G.Polynomial(2) * G.Polynomial(3)
+    rc, out, st = link_and_simulate(G.GraphEvaluator.new(x + x, M), d)
+    assert rc == 0 and st["fused"] == 0 and out == d.direct(x + x, range(3))
 
 
 def test_linker_horner_non_ssa_undefined_and_empty():

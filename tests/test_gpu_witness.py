@@ -176,7 +176,7 @@ def test_cross_term_programs_vs_oracle(W, T, n_gates):
     for p in progs:
         got, st = gpu_eval(W, FR, p, gd)
         assert got == O.eval_rows(FR, pack_program(p), db)
-        assert st["muls"] == p.counts()["mul"] and st["slots"] <= 64
+        assert st["muls"] == p.counts()["mul"] and st["slots"] <= 64 and st["fused"] > 0
 
 
 def test_golden_eval_vectors(W):
