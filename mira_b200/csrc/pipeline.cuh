@@ -1,6 +1,7 @@
 // pipeline.cuh — host orchestration of the MSM pipeline, templated on <coordinate field, scalar field>.
 // Instantiated once per curve (curve_bn254.cu, curve_grumpkin.cu) so the two curves compile in parallel.
 #pragma once
+#include <cstdlib>
 #include "ctx.hpp"
 #include "msm_kernels.cuh"
 #include "testgen.cuh"
@@ -149,11 +150,16 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
   if (pt) pt->mark(2);
   // ---- accumulate
   {
-    // Entries per thread: as long as possible (each chunk edge that falls inside a bucket's run costs one
-    // XYZZ full add in k_combine) while keeping >= ~4 waves of 148 SMs x 512 resident threads.  Sized from
-    // the upper bound n*W; grids cover that bound and surplus threads exit on the device-side pair count.
-    int L = (int)(E / (148u * 512u * 4u));
-    L = L < 16 ? 16 : (L > 256 ? 256 : L);
+    // Entries per thread: as long as possible (each chunk edge that falls inside a bucket's run costs one XYZZ full
+    // add in k_combine, and a thread's first pair pays its load latency alone) while keeping the machine full: two
+    // waves of 148 SMs x 512 resident threads below 32 M pairs, four above, never fewer than 32 pairs per thread
+    // (measured sweep, 2^16..2^22 points: 2^19 2.07 -> 1.64 ms, 2^16 0.40 -> 0.30 ms against the former 4 waves / 16).
+    // Sized from the upper bound n*W; grids cover that bound and surplus threads exit on the device-side pair count.
+    static const unsigned waves_env = [] { const char* e = getenv("MIRA_ACC_WAVES"); return e ? (unsigned)atoi(e) : 0u; }();
+    static const int lmin = [] { const char* e = getenv("MIRA_ACC_LMIN"); return e ? atoi(e) : 32; }();
+    const unsigned waves = waves_env ? waves_env : (E < ((size_t)32 << 20) ? 2u : 4u);
+    int L = (int)(E / (148u * 512u * waves));
+    L = L < lmin ? lmin : (L > 256 ? 256 : L);
     uint32_t n_chunks = (uint32_t)((E + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
     k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(skeys, srefs, d_npairs, L, tab->d, ctx->buckets.p,
