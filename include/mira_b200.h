@@ -153,7 +153,8 @@ void mira_eval_program_destroy(mira_eval_program *prog);
  * PlonkEvalDomain::eval_advice_var (src/plonk/eval.rs:153-228: W1s / W2s, lookup sub-columns). */
 typedef struct {
   uint64_t row_size;            /* GetDataForEval::row_size() */
-  uint32_t num_selectors, num_fixed, num_advice, num_lookup, num_challenges, num_w1, num_w2, _pad;
+  uint32_t num_selectors, num_fixed, num_advice, num_lookup, num_challenges, num_w1, num_w2;
+  uint32_t flags;               /* MIRA_EVAL_LOOKUP_DOMAIN: see below */
   const void *const *selectors; /* [num_selectors] -> row_size bytes, Rust Vec<bool> image (0 / 1) */
   const void *const *fixed;     /* [num_fixed]     -> row_size x 32 B */
   const void *const *w1;        /* W1s[i] */
@@ -163,6 +164,11 @@ typedef struct {
   const void *challenges;       /* num_challenges x 32 B: U1.challenges | U1.u | U2.challenges | 1
                                    (src/nifs/vanilla/mod.rs:91) */
 } mira_eval_domain;
+
+/* flags bit 0: the domain is a LookupEvalDomain (src/plonk/eval.rs:84-135, used by evaluate_ls / evaluate_ts,
+ * src/plonk/lookup.rs:212-276): advice variable `index` is the separate column w1[index] (w1_len[index] rows)
+ * instead of a slice of the concatenated W; w2 is unused. */
+enum { MIRA_EVAL_LOOKUP_DOMAIN = 1 };
 
 /* out_dev[row] = evaluator.evaluate(&domain, row) for row in [0, row_size)
  * (the `(0..row_size).into_par_iter().map(..)` of src/nifs/vanilla/mod.rs:109-116).
@@ -185,6 +191,16 @@ typedef struct {
 } mira_eval_stats;
 /* statistics of the last mira_eval_rows binding of this program */
 int mira_eval_program_stats(const mira_eval_program *prog, mira_eval_stats *out);
+
+/* ---- lookup argument of the SPS rounds 2 / 3 (src/plonk/mod.rs:748-907, src/plonk/lookup.rs:278-319) ----
+ * evaluate_m: out_m[i] = F::from(#{ j : l[j] == t[i] }) at the first occurrence of each distinct t value, ZERO at
+ * later duplicates (the reference's `processed_t`).  Exact: equality is checked on the 32 bytes of the elements. */
+int mira_lookup_m(int field, const void *l_dev, size_t n_l, const void *t_dev, size_t n_t, void *out_m_dev,
+                  int device, void *stream);
+/* evaluate_h_g: out_h[i] = 1 / (l[i] + r), out_g[i] = m[i] / (t[i] + r), with 0 for a zero denominator
+ * (`invert().unwrap_or(ZERO)`).  r_host: 32 B on the host.  Batched inversion (Montgomery's trick) on the device. */
+int mira_lookup_h_g(int field, const void *l_dev, const void *t_dev, const void *m_dev, size_t n, const void *r_host,
+                    void *out_h_dev, void *out_g_dev, int device, void *stream);
 
 /* ---- fft::best_fft (src/fft.rs:51-115): in-place radix-2 transform of 2^log_n elements ------------
  * omega_host: 32 B element of multiplicative order 2^log_n (host).  Output order and values are those of

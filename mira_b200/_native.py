@@ -21,6 +21,7 @@ MIRA_ERR_EVAL_ROW = -13
 MIRA_ERR_EVAL_WITNESS_INDEX = -14
 MIRA_ERR_EVAL_PROGRAM = -15
 MIRA_FQ, MIRA_FR = 0, 1
+MIRA_EVAL_LOOKUP_DOMAIN = 1
 
 # every symbol include/mira_b200.h declares (tests/test_capi_symbols.py checks the .so exports them all)
 SYMBOLS = [
@@ -29,7 +30,7 @@ SYMBOLS = [
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_msm_set_slice_min", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
-    "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_fft", "mira_fft_std", "mira_test_eval_link",
+    "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_lookup_m", "mira_lookup_h_g", "mira_fft", "mira_fft_std", "mira_test_eval_link",
 ]
 _VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy")
 
@@ -38,7 +39,7 @@ class EvalDomain(C.Structure):
     """mira_eval_domain (include/mira_b200.h) == PlonkEvalDomain (src/plonk/eval.rs:93-106)."""
     _fields_ = [("row_size", C.c_uint64), ("num_selectors", C.c_uint32), ("num_fixed", C.c_uint32),
                 ("num_advice", C.c_uint32), ("num_lookup", C.c_uint32), ("num_challenges", C.c_uint32),
-                ("num_w1", C.c_uint32), ("num_w2", C.c_uint32), ("_pad", C.c_uint32),
+                ("num_w1", C.c_uint32), ("num_w2", C.c_uint32), ("flags", C.c_uint32),
                 ("selectors", C.c_void_p), ("fixed", C.c_void_p), ("w1", C.c_void_p), ("w1_len", C.c_void_p),
                 ("w2", C.c_void_p), ("w2_len", C.c_void_p), ("challenges", C.c_void_p)]
 
@@ -107,6 +108,8 @@ def lib():
     L.mira_eval_program_stats.argtypes = [vp, C.POINTER(EvalStats)]
     u32p = C.POINTER(C.c_uint32)
     L.mira_test_eval_link.argtypes = [vp, C.POINTER(EvalDomain), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), u32p, u32p, u32p]
+    L.mira_lookup_m.argtypes = [i, vp, sz, vp, sz, vp, i, vp]
+    L.mira_lookup_h_g.argtypes = [i, vp, vp, vp, sz, vp, vp, vp, i, vp]
     L.mira_fft.argtypes = [i, vp, C.c_uint32, vp, i, vp]
     L.mira_fft_std.argtypes = [i, vp, C.c_uint32, i, i, vp]
     for name in SYMBOLS:

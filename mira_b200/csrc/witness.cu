@@ -231,6 +231,125 @@ __global__ void __launch_bounds__(256) k_scale(void* a, size_t n, const void* __
   fe_store<F>(p, fe_mul(fe_load<F>(p), d));
 }
 
+// ------------------------------------------------------------------ lookup argument (row a6)
+// evaluate_m (src/plonk/lookup.rs:278-305) with two open-addressing hash tables in HBM keyed by the full 256-bit
+// element (a slot remembers one representative INDEX; equality is checked on the 32 input bytes, so there are no
+// false matches): table L counts the occurrences of every distinct l value, table T records the smallest index at
+// which every distinct t value occurs (the reference's `processed_t`: later duplicates report ZERO).
+__device__ __forceinline__ uint32_t lk_hash(const uint4& lo, const uint4& hi) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    h ^= w[i];
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 29;
+  }
+  return (uint32_t)(h ^ (h >> 32));
+}
+__device__ __forceinline__ bool lk_eq(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return ((a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w)) == 0;
+}
+// Finds (or, with insert, claims) the slot of element `v` = vals[i].  rep[s] = representative index + 1, 0 = empty.
+__device__ __forceinline__ int lk_probe(const void* __restrict__ vals, uint32_t i, uint32_t* rep, uint32_t mask, bool insert) {
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(vals) + (size_t)i * 32);
+  uint4 v0 = p[0], v1 = p[1];
+  uint32_t s = lk_hash(v0, v1) & mask;
+  for (;;) {
+    uint32_t cur = reinterpret_cast<volatile uint32_t*>(rep)[s];
+    if (cur == 0) {
+      if (!insert) return -1;
+      cur = atomicCAS(&rep[s], 0u, i + 1);
+      if (cur == 0) return (int)s;
+    }
+    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(vals) + (size_t)(cur - 1) * 32);
+    if (lk_eq(v0, v1, q[0], q[1])) return (int)s;
+    s = (s + 1) & mask;
+  }
+}
+// same, but the probed element comes from another vector than the table's representatives
+__device__ __forceinline__ int lk_find(const void* __restrict__ probe_vals, uint32_t i, const void* __restrict__ table_vals,
+                                       const uint32_t* __restrict__ rep, uint32_t mask) {
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(probe_vals) + (size_t)i * 32);
+  uint4 v0 = p[0], v1 = p[1];
+  uint32_t s = lk_hash(v0, v1) & mask;
+  for (;;) {
+    uint32_t cur = rep[s];
+    if (cur == 0) return -1;
+    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(table_vals) + (size_t)(cur - 1) * 32);
+    if (lk_eq(v0, v1, q[0], q[1])) return (int)s;
+    s = (s + 1) & mask;
+  }
+}
+__global__ void __launch_bounds__(256) k_lookup_count_l(const void* __restrict__ l, uint32_t n_l, uint32_t* rep, uint32_t* cnt, uint32_t mask) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_l) return;
+  int s = lk_probe(l, i, rep, mask, true);
+  atomicAdd(&cnt[s], 1u);
+}
+__global__ void __launch_bounds__(256) k_lookup_first_t(const void* __restrict__ t, uint32_t n_t, uint32_t* rep, uint32_t* first, uint32_t mask) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_t) return;
+  int s = lk_probe(t, i, rep, mask, true);
+  atomicMin(&first[s], i);
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_lookup_m(const void* __restrict__ l, const void* __restrict__ t, uint32_t n_t,
+                                                  const uint32_t* __restrict__ rep_l, const uint32_t* __restrict__ cnt_l, uint32_t mask_l,
+                                                  uint32_t* rep_t, const uint32_t* __restrict__ first_t, uint32_t mask_t,
+                                                  void* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_t) return;
+  Fe<F> m = fe_zero<F>();
+  int st = lk_probe(t, i, rep_t, mask_t, false);
+  if (st >= 0 && first_t[st] == i) {                    // first occurrence of this t value
+    int sl = lk_find(t, i, l, rep_l, mask_l);
+    if (sl >= 0) {
+      m.v[0] = cnt_l[sl];
+      m = fe_from_canonical(m);                         // F::from_u128(count)
+    }
+  }
+  fe_store<F>(reinterpret_cast<char*>(out) + (size_t)i * 32, m);
+}
+
+// out[i] = mul[i] * (in[i] + r)^{-1}  (mul == nullptr: 1), 0 when in[i] + r == 0  (evaluate_h_g, lookup.rs:307-319).
+// Thread t owns elements t, t + T, t + 2T, ... (coalesced), K at a time: Montgomery's trick — prefix products, ONE
+// inversion, back-substitution — so an element costs ~3 products plus 1/K of an inversion.
+constexpr int INV_K = 16;
+template <class F>
+__global__ void __launch_bounds__(128) k_shift_inv_mul(const void* __restrict__ in, const void* __restrict__ mul, size_t n, Fe<F> r,
+                                                       void* __restrict__ out) {
+  const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t base = t; base < n; base += T * INV_K) {
+    Fe<F> pre[INV_K];                                   // pre[k] = product of the non-zero denominators before k
+    Fe<F> acc = fe_one<F>();
+#pragma unroll
+    for (int k = 0; k < INV_K; k++) {
+      size_t i = base + (size_t)k * T;
+      pre[k] = acc;
+      if (i < n) {
+        Fe<F> d = fe_add(fe_load<F>(reinterpret_cast<const char*>(in) + i * 32), r);
+        if (!fe_is_zero(d)) acc = fe_mul(acc, d);
+      }
+    }
+    Fe<F> inv = fe_inv(acc);
+#pragma unroll
+    for (int k = INV_K - 1; k >= 0; k--) {
+      size_t i = base + (size_t)k * T;
+      if (i < n) {
+        Fe<F> d = fe_add(fe_load<F>(reinterpret_cast<const char*>(in) + i * 32), r);
+        Fe<F> res = fe_zero<F>();
+        if (!fe_is_zero(d)) {
+          res = fe_mul(inv, pre[k]);                    // 1 / d
+          inv = fe_mul(inv, d);
+          if (mul) res = fe_mul(res, fe_load<F>(reinterpret_cast<const char*>(mul) + i * 32));
+        }
+        fe_store<F>(reinterpret_cast<char*>(out) + i * 32, res);
+      }
+    }
+  }
+}
+
 }  // namespace mira
 
 // =================================================================================== host side
@@ -315,6 +434,12 @@ struct Linker {
   }
   // PlonkEvalDomain::eval_advice_var (src/plonk/eval.rs:153-228); row-independent part, bounds for the last row
   int advice(size_t index, int32_t rot, Opnd* out) {
+    if (D.flags & MIRA_EVAL_LOOKUP_DOMAIN) {     // LookupEvalDomain::eval_advice_var (src/plonk/eval.rs:125-135)
+      if (index >= D.num_w1) return fail(MIRA_ERR_EVAL_COLUMN, "column variable index out of boundary: %zu", index);
+      if (D.w1_len[index] < D.row_size) return fail(MIRA_ERR_EVAL_ROW, "column variable row index out of boundary: %llu", (unsigned long long)D.w1_len[index]);
+      *out = Opnd{DK_ACCESS, add_access(D.w1[index], rot, false)};
+      return MIRA_OK;
+    }
     size_t row_size = D.row_size, num_advice = D.num_advice, num_lookup = D.num_lookup;
     size_t max_width = num_advice + num_lookup * 5;
     bool first = index < max_width;
@@ -669,6 +794,34 @@ static int fft_impl(void* a, uint32_t log_n, const void* d_consts, bool scale, c
   return MIRA_OK;
 }
 
+// ---- lookup argument ---------------------------------------------------------------------------------
+template <class F>
+static int lookup_m_impl(const void* l, size_t n_l, const void* t, size_t n_t, void* out, cudaStream_t st) {
+  auto cap_for = [](size_t n) { size_t c = 64; while (c < 2 * n) c <<= 1; return c; };
+  const size_t cl = cap_for(n_l), ct = cap_for(n_t);
+  uint32_t* buf = nullptr;                 // rep_l | cnt_l | rep_t | first_t
+  CU(cudaMallocAsync((void**)&buf, (2 * cl + 2 * ct) * 4, st));
+  uint32_t *rep_l = buf, *cnt_l = buf + cl, *rep_t = buf + 2 * cl, *first_t = buf + 2 * cl + ct;
+  CU(cudaMemsetAsync(buf, 0, (2 * cl + ct) * 4, st));
+  CU(cudaMemsetAsync(first_t, 0xff, ct * 4, st));
+  if (n_l) mira::k_lookup_count_l<<<(unsigned)((n_l + 255) / 256), 256, 0, st>>>(l, (uint32_t)n_l, rep_l, cnt_l, (uint32_t)cl - 1);
+  mira::k_lookup_first_t<<<(unsigned)((n_t + 255) / 256), 256, 0, st>>>(t, (uint32_t)n_t, rep_t, first_t, (uint32_t)ct - 1);
+  mira::k_lookup_m<F><<<(unsigned)((n_t + 255) / 256), 256, 0, st>>>(l, t, (uint32_t)n_t, rep_l, cnt_l, (uint32_t)cl - 1, rep_t, first_t,
+                                                                     (uint32_t)ct - 1, out);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(buf, st);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "lookup_m launch failed: %s", cudaGetErrorString(e));
+  return MIRA_OK;
+}
+
+template <class F>
+static int shift_inv_impl(const void* in, const void* mul, size_t n, const void* r, void* out, cudaStream_t st) {
+  size_t threads = (n + mira::INV_K - 1) / mira::INV_K;
+  mira::k_shift_inv_mul<F><<<grid_for(threads, 128, 8), 128, 0, st>>>(in, mul, n, fe_from_host<F>(r), out);
+  CU(cudaGetLastError());
+  return MIRA_OK;
+}
+
 }  // namespace mira_host
 
 using namespace mira_host;
@@ -799,6 +952,31 @@ int mira_eval_program_stats(const mira_eval_program* prog, mira_eval_stats* out)
   if (!prog || !out) return fail(MIRA_ERR_INVALID, "null argument");
   *out = prog->stats;
   return MIRA_OK;
+}
+
+int mira_lookup_m(int field, const void* l, size_t n_l, const void* t, size_t n_t, void* out_m, int device, void* stream) {
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if ((n_l && !l) || (n_t && (!t || !out_m))) return fail(MIRA_ERR_INVALID, "null argument");
+  if (n_l >= ((size_t)1 << 30) || n_t >= ((size_t)1 << 30)) return fail(MIRA_ERR_INVALID, "lookup vectors too long");
+  int rc = set_device(device);
+  if (rc || !n_t) return rc;
+  return field == MIRA_FQ ? lookup_m_impl<mira::FqTag>(l, n_l, t, n_t, out_m, (cudaStream_t)stream)
+                          : lookup_m_impl<mira::FrTag>(l, n_l, t, n_t, out_m, (cudaStream_t)stream);
+}
+
+int mira_lookup_h_g(int field, const void* l, const void* t, const void* m, size_t n, const void* r, void* out_h, void* out_g, int device,
+                    void* stream) {
+  if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
+  if (!r || (n && (!l || !t || !m || !out_h || !out_g))) return fail(MIRA_ERR_INVALID, "null argument");
+  int rc = set_device(device);
+  if (rc || !n) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (field == MIRA_FQ) {
+    if ((rc = shift_inv_impl<mira::FqTag>(l, nullptr, n, r, out_h, st))) return rc;
+    return shift_inv_impl<mira::FqTag>(t, m, n, r, out_g, st);
+  }
+  if ((rc = shift_inv_impl<mira::FrTag>(l, nullptr, n, r, out_h, st))) return rc;
+  return shift_inv_impl<mira::FrTag>(t, m, n, r, out_g, st);
 }
 
 int mira_fft(int field, void* a, uint32_t log_n, const void* omega, int device, void* stream) {

@@ -111,6 +111,8 @@ def concatenate_with_padding(cols: Sequence, pad_size: int, device: int = 0, str
 class PlonkEvalDomain:
     """`PlonkEvalDomain` (src/plonk/eval.rs:93-106): columns are CUDA tensors, challenges are host bytes."""
 
+    flags = 0
+
     def __init__(self, num_advice: int, num_lookup: int, challenges: bytes, selectors: Sequence, fixed: Sequence,
                  W1s: Sequence, W2s: Sequence, row_size: Optional[int] = None):
         self.num_advice, self.num_lookup = num_advice, num_lookup
@@ -139,11 +141,21 @@ class PlonkEvalDomain:
                 (C.c_uint64 * max(len(self.W2s), 1))(*[t.numel() // ELEM for t in self.W2s]),
                 C.create_string_buffer(self.challenges, max(len(self.challenges), 1))]
         d = N.EvalDomain(self.row_size, len(self.selectors), len(self.fixed), self.num_advice, self.num_lookup,
-                         len(self.challenges) // ELEM, len(self.W1s), len(self.W2s), 0,
+                         len(self.challenges) // ELEM, len(self.W1s), len(self.W2s), self.flags,
                          C.cast(keep[0], C.c_void_p), C.cast(keep[1], C.c_void_p), C.cast(keep[2], C.c_void_p),
                          C.cast(keep[4], C.c_void_p), C.cast(keep[3], C.c_void_p), C.cast(keep[5], C.c_void_p),
                          C.cast(keep[6], C.c_void_p))
         return d, keep
+
+
+class LookupEvalDomain(PlonkEvalDomain):
+    """`LookupEvalDomain` (src/plonk/eval.rs:84-135): `advice` is a list of separate columns (`&[Vec<F>]`), as
+    `evaluate_ls` / `evaluate_ts` build it (src/plonk/lookup.rs:212-276)."""
+    flags = N.MIRA_EVAL_LOOKUP_DOMAIN
+
+    def __init__(self, num_lookup: int, challenges: bytes, selectors: Sequence, fixed: Sequence, advice: Sequence,
+                 row_size: Optional[int] = None):
+        super().__init__(len(advice), num_lookup, challenges, selectors, fixed, advice, [], row_size)
 
 
 class GraphEvaluator:
@@ -186,6 +198,28 @@ class GraphEvaluator:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------- lookup argument
+def evaluate_m(field: int, l, t, out=None, stream=None):
+    """`Arguments::evaluate_m` (src/plonk/lookup.rs:278-305): multiplicity of every table value among the lookup
+    values, reported at the first occurrence of each distinct table value."""
+    import torch
+    out = torch.empty_like(t) if out is None else out
+    _check(N.lib().mira_lookup_m(field, l.data_ptr(), l.numel() // ELEM, t.data_ptr(), t.numel() // ELEM, out.data_ptr(), _dev(t),
+                                 _stream(stream)))
+    return out
+
+
+def evaluate_h_g(field: int, l, t, r: bytes, m, stream=None):
+    """`Arguments::evaluate_h_g` (src/plonk/lookup.rs:307-319): h = 1/(l + r), g = m/(t + r), zero denominators -> 0."""
+    import torch
+    if not (l.numel() == t.numel() == m.numel()):
+        raise ValueError("zip_eq: l, t and m lengths differ")
+    h, g = torch.empty_like(l), torch.empty_like(t)
+    _check(N.lib().mira_lookup_h_g(field, l.data_ptr(), t.data_ptr(), m.data_ptr(), l.numel() // ELEM, _host32(r), h.data_ptr(),
+                                   g.data_ptr(), _dev(l), _stream(stream)))
+    return h, g
 
 
 # ------------------------------------------------------------------------------------------- FFT

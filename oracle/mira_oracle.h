@@ -87,7 +87,7 @@ size_t oracle_concat_pad(const void *const *cols, const size_t *lens, size_t n_c
 /* PlonkEvalDomain (src/plonk/eval.rs:93-106) as plain pointers; all HOST memory here. */
 typedef struct {
   uint64_t row_size;                 /* GetDataForEval::row_size() */
-  uint32_t num_selectors, num_fixed, num_advice, num_lookup, num_challenges, num_w1, num_w2, _pad;
+  uint32_t num_selectors, num_fixed, num_advice, num_lookup, num_challenges, num_w1, num_w2, flags;
   const void *const *selectors;      /* [num_selectors] -> row_size bytes (Vec<bool>: 0/1 per row) */
   const void *const *fixed;          /* [num_fixed]     -> row_size x 32 B */
   const void *const *w1;             /* W1s[i] */
@@ -97,6 +97,9 @@ typedef struct {
   const void *challenges;            /* num_challenges x 32 B */
 } oracle_eval_domain;
 
+/* flags bit 0: the domain is a LookupEvalDomain (src/plonk/eval.rs:84-135): advice variable `index` is the separate
+ * column w1[index] (w1_len[index] rows) instead of a slice of the concatenated W; w2 is unused. */
+enum { ORACLE_EVAL_LOOKUP_DOMAIN = 1 };
 /* plonk::eval::Error (src/plonk/eval.rs:3-25) */
 enum {
   ORACLE_EVAL_OK = 0,
@@ -119,6 +122,11 @@ int oracle_eval_rows_mt(int field, const uint32_t *code, size_t code_words, cons
 void oracle_fold_w_mt(int field, const void *w1, const void *w2, size_t n, const void *r, int threads, void *out);
 void oracle_fold_e_mt(int field, const void *e, const void *const *terms, size_t n_terms, size_t n, const void *r,
                       int threads, void *out);
+
+/* lookup argument, SURVEY.md 8 row a6 (src/plonk/lookup.rs:278-319) */
+void oracle_lookup_m(int field, const void *l, size_t n_l, const void *t, size_t n_t, void *out_m);
+void oracle_lookup_h_g(int field, const void *l, const void *t, const void *m, size_t n, const void *r, void *out_h,
+                       void *out_g);
 
 /* fft::best_fft (src/fft.rs:51-115) in place over 2^log_n elements, and its helpers / wrappers */
 void oracle_fft(int field, void *a, uint32_t log_n, const void *omega);

@@ -102,6 +102,12 @@ typedef struct {
 /* PlonkEvalDomain::eval_advice_var (src/plonk/eval.rs:153-228) */
 static int advice_var(const ectx *c, size_t row, size_t index, fe *out) {
     const oracle_eval_domain *d = c->d;
+    if (d->flags & ORACLE_EVAL_LOOKUP_DOMAIN) {   /* LookupEvalDomain::eval_advice_var (src/plonk/eval.rs:125-135) */
+        if (index >= d->num_w1) return ORACLE_EVAL_COLUMN_OUT_OF_BOUNDARY;
+        if (row >= d->w1_len[index]) return ORACLE_EVAL_ROW_OUT_OF_BOUNDARY;
+        *out = ((const fe *)d->w1[index])[row];
+        return 0;
+    }
     size_t row_size = d->row_size, num_advice = d->num_advice, num_lookup = d->num_lookup;
     size_t max_width = num_advice + num_lookup * 5;
     int first = index < max_width;
@@ -395,4 +401,67 @@ void oracle_fold_e_mt(int field, const void *e, const void *const *terms, size_t
     wjob j = {0};
     j.kind = 2; j.field = field; j.a = e; j.terms = terms; j.n_terms = n_terms; j.r = r; j.out = out;
     run_jobs(j, n, threads);
+}
+
+/* ------------------------------------------------------------------ lookup argument
+ * Arguments::evaluate_m (src/plonk/lookup.rs:278-305): m_i = number of j with l_j == t_i, reported at the FIRST
+ * occurrence of each distinct t value and ZERO at later duplicates (`processed_t`); equality is equality of
+ * `to_repr()`, i.e. of field elements.  out: n_t elements, F::from_u128(count) in Montgomery form. */
+typedef struct { fe v; size_t idx; } keyed;
+static int keyed_cmp(const void *a_, const void *b_) {
+    const keyed *a = a_, *b = b_;
+    for (int i = 3; i >= 0; i--) {
+        if (a->v.l[i] != b->v.l[i]) return a->v.l[i] < b->v.l[i] ? -1 : 1;
+    }
+    return a->idx < b->idx ? -1 : (a->idx > b->idx ? 1 : 0);
+}
+static int fe_cmp(const fe *a, const fe *b) {
+    for (int i = 3; i >= 0; i--) {
+        if (a->l[i] != b->l[i]) return a->l[i] < b->l[i] ? -1 : 1;
+    }
+    return 0;
+}
+void oracle_lookup_m(int field, const void *l_, size_t n_l, const void *t_, size_t n_t, void *out_) {
+    winit();
+    const field_t *f = &FIELDS[field];
+    const fe *l = l_, *t = t_;
+    fe *out = out_;
+    keyed *ls = malloc(sizeof(keyed) * (n_l ? n_l : 1)), *ts = malloc(sizeof(keyed) * (n_t ? n_t : 1));
+    for (size_t i = 0; i < n_l; i++) { ls[i].v = l[i]; ls[i].idx = i; }
+    for (size_t i = 0; i < n_t; i++) { ts[i].v = t[i]; ts[i].idx = i; }
+    qsort(ls, n_l, sizeof(keyed), keyed_cmp);
+    qsort(ts, n_t, sizeof(keyed), keyed_cmp);
+    size_t lp = 0;
+    for (size_t i = 0; i < n_t;) {
+        size_t j = i;
+        while (j < n_t && fe_cmp(&ts[j].v, &ts[i].v) == 0) j++;          /* group of equal t values, index-sorted */
+        while (lp < n_l && fe_cmp(&ls[lp].v, &ts[i].v) < 0) lp++;
+        size_t q = lp;
+        while (q < n_l && fe_cmp(&ls[q].v, &ts[i].v) == 0) q++;
+        fe_from_u64(f, &out[ts[i].idx], (uint64_t)(q - lp));              /* first occurrence gets the count ... */
+        for (size_t k = i + 1; k < j; k++) memset(&out[ts[k].idx], 0, 32); /* ... later duplicates ZERO          */
+        lp = q;
+        i = j;
+    }
+    free(ls);
+    free(ts);
+}
+
+/* Arguments::evaluate_h_g (src/plonk/lookup.rs:307-319): h_i = 1/(l_i + r), g_i = m_i/(t_i + r); a zero
+ * denominator yields ZERO (`Option::from(x.invert()).unwrap_or(F::ZERO)`). */
+void oracle_lookup_h_g(int field, const void *l_, const void *t_, const void *m_, size_t n, const void *r_, void *h_, void *g_) {
+    winit();
+    const field_t *f = &FIELDS[field];
+    const fe *l = l_, *t = t_, *m = m_;
+    fe *h = h_, *g = g_;
+    fe r;
+    memcpy(&r, r_, 32);
+    for (size_t i = 0; i < n; i++) {
+        fe s, inv;
+        fe_add(f, &s, &l[i], &r);
+        fe_inv(f, &h[i], &s);
+        fe_add(f, &s, &t[i], &r);
+        fe_inv(f, &inv, &s);
+        fe_mul(f, &g[i], &m[i], &inv);
+    }
 }

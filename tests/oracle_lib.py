@@ -44,6 +44,8 @@ def lib():
     L.oracle_concat_pad.restype = sz
     L.oracle_eval_rows.argtypes = [i, vp, sz, vp, sz, vp, sz, C.c_uint32, vp, sz, sz, vp]
     L.oracle_eval_rows.restype = i
+    L.oracle_lookup_m.argtypes = [i, vp, sz, vp, sz, vp]
+    L.oracle_lookup_h_g.argtypes = [i, vp, vp, vp, sz, vp, vp, vp]
     L.oracle_fft.argtypes = [i, vp, C.c_uint32, vp]
     L.oracle_fft_omega.argtypes = [i, C.c_uint32, i, vp]
     L.oracle_fft_omega.restype = i
@@ -160,7 +162,7 @@ class EvalDomainStruct(C.Structure):
     """oracle_eval_domain == mira_eval_domain (same field order)."""
     _fields_ = [("row_size", C.c_uint64), ("num_selectors", C.c_uint32), ("num_fixed", C.c_uint32),
                 ("num_advice", C.c_uint32), ("num_lookup", C.c_uint32), ("num_challenges", C.c_uint32),
-                ("num_w1", C.c_uint32), ("num_w2", C.c_uint32), ("_pad", C.c_uint32),
+                ("num_w1", C.c_uint32), ("num_w2", C.c_uint32), ("flags", C.c_uint32),
                 ("selectors", C.c_void_p), ("fixed", C.c_void_p), ("w1", C.c_void_p), ("w1_len", C.c_void_p),
                 ("w2", C.c_void_p), ("w2_len", C.c_void_p), ("challenges", C.c_void_p)]
 
@@ -187,7 +189,7 @@ def eval_rows(field, prog: dict, dom: dict, row_begin=0, row_end=None) -> bytes:
     ch = dom.get("challenges", b"")
     chb = C.create_string_buffer(ch, max(len(ch), 1))
     d = EvalDomainStruct(dom["row_size"], len(dom.get("selectors", [])), len(dom.get("fixed", [])), dom.get("num_advice", 0),
-                         dom.get("num_lookup", 0), len(ch) // 32, len(dom.get("w1", [])), len(dom.get("w2", [])), 0,
+                         dom.get("num_lookup", 0), len(ch) // 32, len(dom.get("w1", [])), len(dom.get("w2", [])), dom.get("flags", 0),
                          C.cast(sel, C.c_void_p), C.cast(fx, C.c_void_p), C.cast(w1, C.c_void_p), C.cast(l1, C.c_void_p),
                          C.cast(w2, C.c_void_p), C.cast(l2, C.c_void_p), C.cast(chb, C.c_void_p))
     n = max(row_end - row_begin, 0)
@@ -216,3 +218,13 @@ def fft(field, a: bytes, log_n: int) -> bytes:
 
 def ifft(field, a: bytes, log_n: int) -> bytes:
     o = C.create_string_buffer(a, len(a)); assert lib().oracle_fft_inverse(field, o, log_n) == 0; return o.raw[:len(a)]
+
+
+def lookup_m(field, l: bytes, t: bytes) -> bytes:
+    o = _buf(max(len(t), 1)); lib().oracle_lookup_m(field, l, len(l) // 32, t, len(t) // 32, o); return o.raw[:len(t)]
+
+
+def lookup_h_g(field, l: bytes, t: bytes, m: bytes, r: bytes):
+    h, g = _buf(max(len(l), 1)), _buf(max(len(l), 1))
+    lib().oracle_lookup_h_g(field, l, t, m, len(l) // 32, r, h, g)
+    return h.raw[:len(l)], g.raw[:len(l)]

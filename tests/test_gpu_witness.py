@@ -330,3 +330,67 @@ def test_row_range_shards_concatenate_to_the_whole(W):
     with pytest.raises(W.EvalError) as ex:
         prog.evaluate_rows(gd, rows=(0, rows + 1))
     assert ex.value.kind == "RowIndexOutOfBoundary"
+
+
+# ---- lookup argument: SPS rounds 2 / 3 (src/plonk/mod.rs:748-907, src/plonk/lookup.rs:212-319)
+@pytest.mark.parametrize("field,curve,m", [(FR, R.BN254, R.R_), (FQ, R.GRUMPKIN, R.P)])
+def test_lookup_m_and_h_g(W, field, curve, m):
+    rng = random.Random(21)
+    for n_l, n_t in ((1, 1), (300, 64), (5000, 4096), (70_000, 1 << 15)):
+        table = [rng.randrange(m) for _ in range(max(n_t - 6, 1))]
+        t = (table + [0, 1, m - 1, table[0], table[-1], table[-1]])[:n_t]
+        l = [rng.choice(t + [rng.randrange(m)]) for _ in range(n_l)]
+        lb, tb = mont(l, m), mont(t, m)
+        want_m = O.lookup_m(field, lb, tb)
+        ld, td = dev(lb), dev(tb)
+        md = W.evaluate_m(field, ld, td)
+        assert host(md) == want_m
+        n = min(n_l, n_t)
+        r = R.to_mont_bytes((-l[0]) % m, m)                     # a zero denominator in h
+        l2, t2, m2 = dev(lb[:32 * n]), dev(tb[:32 * n]), dev(want_m[:32 * n])
+        h, g = W.evaluate_h_g(field, l2, t2, r, m2)
+        wh, wg = O.lookup_h_g(field, lb[:32 * n], tb[:32 * n], want_m[:32 * n], r)
+        assert host(h) == wh and host(g) == wg and wh[:32] == bytes(32)
+    assert W.evaluate_m(field, dev(b""), dev(tb)).cpu().numpy().tobytes() == bytes(len(tb))
+
+
+def test_sps_round_with_lookup_end_to_end(W):
+    """run_sps_protocol_3's lookup rounds (src/plonk/mod.rs:833-881): l, t evaluated over a LookupEvalDomain, m, then
+    W2 = concat(ls, ts, ms) committed; h, g, then W3 = concat(hs, gs) committed — GPU vs oracle, bit for bit."""
+    from mira_b200 import BN254_G1, CommitmentKey
+    rows = 256
+    d = Domain(M, rows, 1, 2, 3, 0, 1, 1, seed=31)
+    rng = random.Random(32)
+    # make the lookup hold: advice column 0 takes values from fixed column 0 (the table)
+    table = d.fixed[0]
+    cols = [[rng.choice(table) for _ in range(rows)], d.w1[0][rows:2 * rows], d.w1[0][2 * rows:3 * rows]]
+    l_expr = G.Polynomial(3 + 0) + G.Challenge(0) * G.Polynomial(0)             # selector-gated lookup value
+    t_expr = G.Polynomial(1) + G.Challenge(0) * G.Polynomial(0)
+    dom_o = {"row_size": rows, "num_advice": 3, "num_lookup": 1, "selectors": [bytes(s) for s in d.selectors],
+             "fixed": [mont(c, M) for c in d.fixed], "w1": [mont(c, M) for c in cols], "w2": [], "challenges": mont(d.challenges, M),
+             "flags": 1}
+    dom_g = W.LookupEvalDomain(1, dom_o["challenges"], [dev(s) for s in dom_o["selectors"]], [dev(f) for f in dom_o["fixed"]],
+                               [dev(c) for c in dom_o["w1"]], row_size=rows)
+    bases = O.gen_bases(R.BN254, 77, 3 * rows)
+    ck = CommitmentKey(BN254_G1, bases)
+    lt_o, lt_g = [], []
+    for e in (l_expr, t_expr):
+        p = pack_program(G.GraphEvaluator.new(e, M))
+        lt_o.append(O.eval_rows(FR, p, dom_o))
+        prog = W.GraphEvaluator(FR, p["code"], p["constants"], p["rotations"], p["num_intermediates"])
+        lt_g.append(prog.evaluate_rows(dom_g))
+        assert host(lt_g[-1]) == lt_o[-1]
+    m_o = O.lookup_m(FR, lt_o[0], lt_o[1])
+    m_g = W.evaluate_m(FR, lt_g[0], lt_g[1])
+    w2_o = O.concat_pad([lt_o[0], lt_o[1], m_o], rows)
+    w2_g = W.concatenate_with_padding([lt_g[0], lt_g[1], m_g], rows)
+    torch.cuda.synchronize()
+    assert host(w2_g) == w2_o
+    assert ck.commit_device(w2_g.data_ptr(), 3 * rows) == O.commit(R.BN254, bases, w2_o)
+    r2 = O.gen_scalars(R.BN254, 33, 1)
+    h_o, g_o = O.lookup_h_g(FR, lt_o[0], lt_o[1], m_o, r2)
+    h_g, g_g = W.evaluate_h_g(FR, lt_g[0], lt_g[1], r2, m_g)
+    w3_g = W.concatenate_with_padding([h_g, g_g], rows)
+    torch.cuda.synchronize()
+    assert host(w3_g) == O.concat_pad([h_o, g_o], rows)
+    assert ck.commit_device(w3_g.data_ptr(), 2 * rows) == O.commit(R.BN254, bases[:64 * 2 * rows], O.concat_pad([h_o, g_o], rows))

@@ -212,3 +212,62 @@ def test_golden_eval_vectors_freeze_the_oracle():
         p = progs[v["term"] - 1]
         assert len(p.calculations) == v["nodes"]
         assert hashlib.sha256(O.eval_rows(FR, pack_program(p), dom)).hexdigest() == v["sha256"]
+
+
+# ---- lookup argument (src/plonk/lookup.rs:278-319), SPS rounds 2 / 3
+def _lookup_case(m, seed, n_l=400, n_t=128):
+    rng = random.Random(seed)
+    table = [rng.randrange(m) for _ in range(n_t - 8)] + [0, 1, m - 1]
+    t = table + [table[0], table[5], table[5], 0, rng.randrange(m)][: n_t - len(table)]     # duplicates in t
+    l = [rng.choice(table + [rng.randrange(m)]) for _ in range(n_l)]
+    return l, t
+
+
+@pytest.mark.parametrize("field,m", [(FR, R.R_), (FQ, R.P)])
+def test_lookup_m_h_g_vs_python(field, m):
+    l, t = _lookup_case(m, 11)
+    got = unmont(O.lookup_m(field, mont(l, m), mont(t, m)), m)
+    seen, want = set(), []
+    for x in t:                                   # the reference's loop, literally
+        want.append(0 if x in seen else l.count(x))
+        seen.add(x)
+    assert got == want and sum(got) <= len(l) and any(v > 1 for v in got)
+    r = (-l[3]) % m                               # forces a zero denominator
+    n = len(t)
+    h, g = O.lookup_h_g(field, mont(l[:n], m), mont(t, m), mont(got, m), R.to_mont_bytes(r, m))
+    inv = lambda x: pow(x, m - 2, m) if x % m else 0
+    assert unmont(h, m) == [inv((x + r) % m) for x in l[:n]] and 0 in unmont(h, m)
+    assert unmont(g, m) == [c * inv((x + r) % m) % m for x, c in zip(t, got)]
+    assert O.lookup_m(field, b"", mont(t, m)) == bytes(32 * n) and O.lookup_m(field, mont(l, m), b"") == b""
+
+
+def test_log_derivative_identity():
+    """sum_i h_i == sum_i g_i when every l value is in the table (what the lookup argument proves), for the h, g, m
+    the three functions produce together."""
+    m = M
+    rng = random.Random(12)
+    table = [rng.randrange(m) for _ in range(64)]
+    l = [rng.choice(table) for _ in range(64)]
+    ms = O.lookup_m(FR, mont(l, m), mont(table, m))
+    r = R.to_mont_bytes(rng.randrange(m), m)
+    h, g = O.lookup_h_g(FR, mont(l, m), mont(table, m), ms, r)
+    assert sum(unmont(h, m)) % m == sum(unmont(g, m)) % m
+
+
+def test_lookup_eval_domain_uses_separate_advice_columns():
+    """LookupEvalDomain::eval_advice_var (src/plonk/eval.rs:125-135): advice[index][row]."""
+    d = Domain(M, 6, 1, 2, 3, 0, 1, 1, seed=13)
+    cols = [d.w1[0][c * 6:(c + 1) * 6] for c in range(3)]
+    dom = {"row_size": 6, "num_advice": 3, "num_lookup": 1, "selectors": [bytes(s) for s in d.selectors],
+           "fixed": [mont(c, M) for c in d.fixed], "w1": [mont(c, M) for c in cols], "w2": [], "challenges": mont(d.challenges, M),
+           "flags": 1}
+    e = (G.Polynomial(3 + 1) * G.Challenge(0) + G.Polynomial(3 + 2, 1)) * G.Polynomial(1) + G.Polynomial(0)
+    ge = G.GraphEvaluator.new(e, M)
+    assert unmont(O.eval_rows(FR, pack_program(ge), dom), M) == d.direct(e, range(6))
+    with pytest.raises(O.EvalError) as ex:
+        O.eval_rows(FR, pack_program(G.GraphEvaluator.new(G.Polynomial(3 + 3), M)), dom)
+    assert ex.value.rc == -12        # ColumnVariableIndexOutOfBoundary
+    dom["w1"][2] = dom["w1"][2][:32 * 4]
+    with pytest.raises(O.EvalError) as ex:
+        O.eval_rows(FR, pack_program(G.GraphEvaluator.new(G.Polynomial(3 + 2), M)), dom)
+    assert ex.value.rc == -13        # RowIndexOutOfBoundary
