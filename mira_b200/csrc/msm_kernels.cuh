@@ -130,6 +130,9 @@ __device__ __forceinline__ Affine<CF> load_ref(const void* __restrict__ table, u
   return p;
 }
 
+#ifndef MIRA_ACC_PREFETCH
+#define MIRA_ACC_PREFETCH 0
+#endif
 #ifndef MIRA_ACC_MIN_BLOCKS
 #define MIRA_ACC_MIN_BLOCKS 1
 #endif
@@ -169,6 +172,12 @@ __global__ void __launch_bounds__(128, MIRA_ACC_MIN_BLOCKS) k_accumulate(const u
       if (add_mode) acc = xyzz_load_shared<CF>(reinterpret_cast<const char*>(buckets) + (size_t)cur * 128);
       else acc = xyzz_identity<CF>();
     }
+#if MIRA_ACC_PREFETCH
+    if (e + MIRA_ACC_PREFETCH < end) {    // pull the point two adds ahead into L2: the gather is a dependent DRAM access
+      const char* nxt = reinterpret_cast<const char*>(table) + (size_t)(srefs[e + MIRA_ACC_PREFETCH] & ~REF_NEG) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+    }
+#endif
     Affine<CF> p = load_ref<CF>(table, srefs[e]);
     xyzz_madd(acc, p);
   }
