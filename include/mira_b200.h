@@ -106,8 +106,9 @@ int mira_msm_set_profiling(mira_msm_ctx *ctx, int enabled);
 /* override the window width chosen by the size heuristic (0 = automatic). */
 int mira_msm_set_window(mira_msm_ctx *ctx, int window_bits);
 /* Host-buffer commits (mira_msm_commit, mira_msm_partial with host scalars) are pipelined: the vector is cut
- * into up to 4 slices of at least `min_scalars_per_slice` scalars (default 2^21) and slice k+1 crosses PCIe
- * while slice k is accumulated into the same bucket set.  0 disables slicing.  The result does not depend on it. */
+ * into up to 4 slices of geometrically growing size (1 : 4 : 16 : 64), the smallest of at least
+ * `min_scalars_per_slice` scalars (default 2^19), and slice k+1 crosses PCIe while slice k is accumulated into
+ * the same bucket set.  0 disables slicing.  The result does not depend on it. */
 int mira_msm_set_slice_min(mira_msm_ctx *ctx, size_t min_scalars_per_slice);
 
 /* ==== field vectors in HBM: the witness side of the hot path =====

@@ -62,14 +62,14 @@ struct mira_msm_ctx {
   void* d_bases = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // H2D of host-buffer commits, overlapped with compute slice by slice
-  cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t copy_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t compute_idle = nullptr;
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
   void* h_result = nullptr;  // pinned, 4 KiB (up to 32 affine results of a batched commit)
   int forced_window = 0;
-  size_t slice_min = (size_t)1 << 21;          // host-buffer commits are pipelined in up to 4 slices of >= this many scalars
+  size_t slice_min = (size_t)1 << 19;          // host-buffer commits: smallest (first) slice of the geometric H2D pipeline
   bool profiling = false;
   mira_msm_stats stats{};
   std::mutex mu;

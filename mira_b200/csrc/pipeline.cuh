@@ -1,6 +1,7 @@
 // pipeline.cuh — host orchestration of the MSM pipeline, templated on <coordinate field, scalar field>.
 // Instantiated once per curve (curve_bn254.cu, curve_grumpkin.cu) so the two curves compile in parallel.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "ctx.hpp"
 #include "msm_kernels.cuh"
@@ -266,9 +267,36 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
     return MIRA_OK;
   }
   if ((rc = ctx->scalars.ensure(n * 32))) return rc;
-  int K = (int)(n / (ctx->slice_min ? ctx->slice_min : 1));
-  K = K < 1 ? 1 : (K > SLICE_MAX_COUNT ? SLICE_MAX_COUNT : K);
-  size_t per = ((n + K - 1) / K + 255) & ~(size_t)255;
+  // Slice sizes grow geometrically (1 : 4 : 16 : 64): accumulating a slice takes ~4x as long as copying it, so every
+  // copy but the first hides behind the previous slice's compute and the exposed first copy is as small as
+  // ctx->slice_min allows (2^24 scalars: 3 slices, 0.8 M first => ~0.5 ms of the 9.7 ms H2D stays visible).
+  int K = 1;
+  {
+    size_t weight = 1, sum = 1;
+    while (K < SLICE_MAX_COUNT && ctx->slice_min && n / (sum + weight * 4) >= ctx->slice_min) {
+      weight *= 4;
+      sum += weight;
+      K++;
+    }
+  }
+  size_t bounds[SLICE_MAX_COUNT + 2];
+  int n_slices = 0;
+  bounds[0] = 0;
+  {
+    size_t total_w = 0, w = 1;
+    for (int k = 0; k < K; k++, w *= 4) total_w += w;
+    size_t pos = 0;
+    w = 1;
+    for (int k = 0; k < K - 1; k++, w *= 4) {
+      size_t len = ((n * w / total_w) + 255) & ~(size_t)255;
+      if (pos + len >= n) break;
+      pos += len;
+      bounds[++n_slices] = pos;
+    }
+    bounds[++n_slices] = n;
+  }
+  size_t max_slice = 0;
+  for (int k = 0; k < n_slices; k++) max_slice = std::max(max_slice, bounds[k + 1] - bounds[k]);
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int k = 0; k < SLICE_MAX_COUNT; k++)
     if (!ctx->copy_done[k]) CU(cudaEventCreateWithFlags(&ctx->copy_done[k], cudaEventDisableTiming));
@@ -276,18 +304,16 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   // the copies must not overtake work already queued on `st` that still reads ctx->scalars (a previous commit)
   CU(cudaEventRecord(ctx->compute_idle, st));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_idle, 0));
-  int n_slices = 0;
-  for (size_t first = 0; first < n; first += per, n_slices++) {
-    size_t cnt = n - first < per ? n - first : per;
+  for (int k = 0; k < n_slices; k++) {
+    size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
     CU(cudaMemcpyAsync((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, cudaMemcpyHostToDevice,
                        ctx->copy_stream));
-    CU(cudaEventRecord(ctx->copy_done[n_slices], ctx->copy_stream));
+    CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
   }
   MsmPlan plan;
-  if ((rc = msm_begin<CF>(ctx, n, per < n ? per : n, st, &plan))) return rc;
-  int k = 0;
-  for (size_t first = 0; first < n; first += per, k++) {
-    size_t cnt = n - first < per ? n - first : per;
+  if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan))) return rc;
+  for (int k = 0; k < n_slices; k++) {
+    size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
     CU(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
     const void* sets[1] = {(const char*)ctx->scalars.p + first * 32};
     if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, first, cnt, k > 0, st, nullptr))) return rc;
