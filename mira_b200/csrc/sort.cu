@@ -28,6 +28,9 @@ constexpr int RS_ITEMS = MIRA_RS_ITEMS;            // pairs per thread
 // Tile geometry: THREADS x RS_ITEMS pairs per tile.  Measured at 2^24 points (3 passes, ms): 256x16 5.61, 256x8 5.51,
 // 384x8 5.17, 512x8 4.91 (shipped), 512x4 6.02, 768x4 6.05, 1024x4 5.67, 1024x8 6.09.  ncu (profiles/r01_msm_aux_v7.txt): the scatter is
 // latency-bound (46 % of stall samples wait for the tile's own key loads), not bandwidth-bound (24 % of HBM peak).
+// A persistent variant that prefetched the NEXT tile (keys in registers, values via a cp.async double buffer) was
+// measured SLOWER (5.7 vs 4.9 ms): nothing is saturated (L1/smem 51 %, L2 19 %, DRAM 24 %, issue 41 %), the five
+// block-wide barriers per tile are what serialises it; a one-sweep design with decoupled look-back is the next step.
 template <int THREADS> struct RsCfg {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int TILE = THREADS * RS_ITEMS;
