@@ -90,6 +90,14 @@ int mira_msm_partial(mira_msm_ctx *ctx, const void *scalars, size_t n, int scala
 /* out_affine (HOST, 64 B) = to_affine( sum of `count` XYZZ partials (HOST, 128 B each) ), on `device`. */
 int mira_msm_combine(int curve, const void *partials_xyzz, size_t count, int device, void *out_affine);
 
+/* Page-lock a host buffer the caller will commit from repeatedly (a witness column arena, the `Vec<C::Scalar>` a
+ * prover re-uses every step).  mira_msm_commit works with any host memory, but only page-locked memory lets the
+ * H2D copies of its slices run asynchronously at PCIe speed behind the accumulation of the previous slice; with
+ * pageable memory the driver stages every copy through its own buffers, synchronously.  Thin wrappers over
+ * cudaHostRegister / cudaHostUnregister; registering an already registered range is not an error. */
+int mira_host_register(void *host_ptr, size_t bytes);
+int mira_host_unregister(void *host_ptr);
+
 /* ---- introspection used by bench.py / DESIGN.md roofline accounting ------------------------------ */
 typedef struct {
   int window_bits;        /* c: signed window width of the last commit */

@@ -173,6 +173,23 @@ int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
   return MIRA_OK;
 }
 
+int mira_host_register(void* host_ptr, size_t bytes) {
+  if (!host_ptr || !bytes) return fail(MIRA_ERR_INVALID, "null argument");
+  cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return MIRA_OK;
+  }
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  return MIRA_OK;
+}
+int mira_host_unregister(void* host_ptr) {
+  if (!host_ptr) return fail(MIRA_ERR_INVALID, "null argument");
+  cudaError_t e = cudaHostUnregister(host_ptr);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+  return MIRA_OK;
+}
+
 int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
   ctx->slice_min = min_scalars_per_slice ? min_scalars_per_slice : ~(size_t)0;   // 0 = never slice
