@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/mira_b200.h"
+#include "stager.hpp"
 
 namespace mira_host {
 
@@ -64,6 +65,7 @@ struct mira_msm_ctx {
   cudaStream_t copy_stream = nullptr;          // H2D of host-buffer commits, overlapped with compute slice by slice
   cudaEvent_t copy_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t compute_idle = nullptr;
+  mira_host::Stager stager;                    // pageable host scalars go through page-locked slots (stager.hpp)
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;

@@ -102,6 +102,7 @@ void mira_msm_ctx_destroy(mira_msm_ctx* ctx) {
   for (auto& e : ctx->copy_done)
     if (e) cudaEventDestroy(e);
   if (ctx->compute_idle) cudaEventDestroy(ctx->compute_idle);
+  ctx->stager.release();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

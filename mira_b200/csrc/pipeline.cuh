@@ -304,16 +304,29 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   // the copies must not overtake work already queued on `st` that still reads ctx->scalars (a previous commit)
   CU(cudaEventRecord(ctx->compute_idle, st));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_idle, 0));
-  for (int k = 0; k < n_slices; k++) {
-    size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
-    CU(cudaMemcpyAsync((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, cudaMemcpyHostToDevice,
-                       ctx->copy_stream));
-    CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
-  }
+  // page-locked source: all copies are queued now and run by the copy engine on their own;
+  // pageable source (a plain Rust Vec): each slice is staged through page-locked slots by worker threads right
+  // before its compute is queued, so the staging of slice k+1 overlaps the accumulation of slice k
+  cudaPointerAttributes attr{};
+  bool pageable = true;
+  if (cudaPointerGetAttributes(&attr, h_scalars) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+  else cudaGetLastError();
+  if (pageable) CU(ctx->stager.init());
+  if (!pageable)
+    for (int k = 0; k < n_slices; k++) {
+      size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
+      CU(cudaMemcpyAsync((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, cudaMemcpyHostToDevice,
+                         ctx->copy_stream));
+      CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
+    }
   MsmPlan plan;
   if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan))) return rc;
   for (int k = 0; k < n_slices; k++) {
     size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
+    if (pageable) {
+      CU(ctx->stager.copy((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, ctx->copy_stream));
+      CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
+    }
     CU(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
     const void* sets[1] = {(const char*)ctx->scalars.p + first * 32};
     if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, first, cnt, k > 0, st, nullptr))) return rc;
