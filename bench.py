@@ -364,12 +364,11 @@ def run_fold_step(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(g.stream)
-        for prog, tt in zip(t["progs"], t["T"]):
-            prog.evaluate_rows(dom, out=tt, stream=g.stream.cuda_stream)
+        W.evaluate_rows_multi(t["progs"], dom, outs=t["T"], stream=g.stream.cuda_stream)
         e1.record(g.stream)
         torch.cuda.synchronize()
         ev_ms += e0.elapsed_time(e1)
-        muls += s["muls_per_row"] * s["rows"]
+        muls += t["progs"][0].stats()["muls"] * s["rows"]        # products actually executed by the merged program
     imad_peak = 148 * IMAD_WIDE_PER_CLK_PER_SM * sm_max * 1e6
     pts = F.points_per_step(sh)
     h2d = sum(s["n_w"] * 32 for s in sh)
@@ -386,7 +385,7 @@ def run_fold_step(args):
            "e2e": {"value": round(ms_e2e, 3), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64 * ncommit},
            "gpu_launches": (ncommit * launches // max(len(st), 1) + g.launches_per_step()) * args.steps,
            "phases_ms": {"cross_term_evaluation": round(ev_ms, 3), "commits_and_fold": round(ms_dev - ev_ms, 3)},
-           "roofline": {"kernel": "k_eval_rows (all 11 cross-term programs)", "bound": "hbm", "achieved": None, "peak": hbm_peak,
+           "roofline": {"kernel": "k_eval_rows (all 11 cross-term programs, merged per circuit)", "bound": "hbm", "achieved": None, "peak": hbm_peak,
                         "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
                         "note": "integer-pipe bound kernel, see roofline_imad; the MSM kernels' roofline is in the default workload's line"},
            "roofline_imad": {"kernel": "k_eval_rows", "bound": "imad.wide.u32", "achieved": round(muls * MACS_PER_MODMUL / (ev_ms * 1e-3) / 1e12, 3),

@@ -189,6 +189,14 @@ int mira_eval_rows(const mira_eval_program *prog, const mira_eval_domain *dom, v
  * commits it against its slice of the key; row_end > row_size is RowIndexOutOfBoundary. */
 int mira_eval_rows_range(const mira_eval_program *prog, const mira_eval_domain *dom, uint64_t row_begin,
                          uint64_t row_end, void *out_dev, int device, void *stream);
+/* All cross terms of a fold in ONE launch: `n_progs` (<= 16) programs over the same domain, outs_dev[k] receiving
+ * program k's vector (HOST array of device pointers).  The programs are merged by value numbering — the reference
+ * builds one GraphEvaluator per cross term (src/nifs/vanilla/mod.rs:100-121) but the terms share most of their
+ * sub-products (63 % of the multiplications of the primary IVC circuit's six terms) — so a shared value is computed
+ * once per row.  Field arithmetic is exact: every output is bit-identical to evaluating its program alone.
+ * Programs whose targets are re-assigned cannot be merged (MIRA_ERR_EVAL_PROGRAM); evaluate those one by one. */
+int mira_eval_rows_multi(const mira_eval_program *const *progs, size_t n_progs, const mira_eval_domain *dom,
+                         uint64_t row_begin, uint64_t row_end, void *const *outs_dev, int device, void *stream);
 typedef struct {
   uint32_t instructions;   /* device instructions after Store-forwarding and Horner expansion */
   uint32_t slots;          /* live intermediates kept per row (local memory) */
@@ -198,7 +206,7 @@ typedef struct {
   uint32_t loads;          /* column loads executed per row */
   uint32_t fused;          /* a*b +- c*d pairs executed as one dual-product instruction (counted in muls/adds too) */
 } mira_eval_stats;
-/* statistics of the last mira_eval_rows binding of this program */
+/* statistics of the last binding that involved this program (of the MERGED program after a multi call) */
 int mira_eval_program_stats(const mira_eval_program *prog, mira_eval_stats *out);
 
 /* ---- lookup argument of the SPS rounds 2 / 3 (src/plonk/mod.rs:748-907, src/plonk/lookup.rs:278-319) ----
@@ -235,14 +243,17 @@ int mira_test_field_op(int field, int op, const void *a, const void *b, size_t n
  * op: 0 p+q via XYZZ mixed add, 1 p+q via XYZZ full add, 2 2p, 3 k*p with k = (uint32) first word of q */
 int mira_test_point_op(int curve, int op, const void *p, const void *q, size_t n, int device, void *out);
 
-/* Host-only unit-test hook: binds `prog` to `dom` (pointers are only recorded, never dereferenced) and returns
- * the linked device program, so the CPU test-suite can check the linker (Store forwarding, Horner expansion,
- * liveness-based slot allocation) without a GPU.  instr_words: 4 u32 per device instruction
- * (op | akind << 4 | bkind << 8 | dst << 16, a, b, 0; kinds 0 slot, 1 uniform, 2 access); access_words: 3 u64 per
- * access (column pointer, rotation as i64, is_selector).  Uniform i is constants[i], then the challenges, then ZERO. */
-int mira_test_eval_link(const mira_eval_program *prog, const mira_eval_domain *dom, uint32_t *instr_words,
-                        size_t instr_cap, size_t *n_instr, uint64_t *access_words, size_t access_cap, size_t *n_access,
-                        uint32_t *result_kind, uint32_t *result_idx, uint32_t *n_slots);
+/* Host-only unit-test hook: binds the programs to `dom` (pointers are only recorded, never dereferenced) and returns
+ * the linked device program, so the CPU test-suite can check the linker (Store forwarding, Horner expansion, value
+ * numbering across programs, product-pair fusion, liveness-based slot allocation) without a GPU.
+ * instr_words: 4 u32 per device instruction (op | akind << 4 | bkind << 8 | dst << 16, a, b, c | ckind << 14 | d << 16 |
+ * dkind << 30; kinds 0 slot, 1 uniform, 2 access; ops 0 add 1 sub 2 mul 3 square 4 double 5 negate 6 copy 7 a*b+c*d
+ * 8 a*b-c*d 9 out[dst] = a); access_words: 3 u64 per access (column pointer, rotation as i64, is_selector);
+ * uniform_bytes: n_uniforms x 32 B (constants, challenges, then ZERO). */
+int mira_test_eval_link_multi(const mira_eval_program *const *progs, size_t n_progs, const mira_eval_domain *dom,
+                              uint32_t *instr_words, size_t instr_cap, size_t *n_instr, uint64_t *access_words,
+                              size_t access_cap, size_t *n_access, void *uniform_bytes, size_t uniform_cap,
+                              size_t *n_uniforms, uint32_t *n_slots);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ SYMBOLS = [
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_msm_set_slice_min", "mira_host_register", "mira_host_unregister", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
-    "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_lookup_m", "mira_lookup_h_g", "mira_fft", "mira_fft_std", "mira_test_eval_link",
+    "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_lookup_m", "mira_lookup_h_g", "mira_fft", "mira_fft_std", "mira_test_eval_link_multi", "mira_eval_rows_multi",
 ]
 _VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy")
 
@@ -109,7 +109,9 @@ def lib():
     L.mira_eval_rows_range.argtypes = [vp, C.POINTER(EvalDomain), C.c_uint64, C.c_uint64, vp, i, vp]
     L.mira_eval_program_stats.argtypes = [vp, C.POINTER(EvalStats)]
     u32p = C.POINTER(C.c_uint32)
-    L.mira_test_eval_link.argtypes = [vp, C.POINTER(EvalDomain), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), u32p, u32p, u32p]
+    L.mira_test_eval_link_multi.argtypes = [vp, sz, C.POINTER(EvalDomain), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), vp, sz,
+                                            C.POINTER(sz), u32p]
+    L.mira_eval_rows_multi.argtypes = [vp, sz, C.POINTER(EvalDomain), C.c_uint64, C.c_uint64, vp, i, vp]
     L.mira_lookup_m.argtypes = [i, vp, sz, vp, sz, vp, i, vp]
     L.mira_lookup_h_g.argtypes = [i, vp, vp, vp, sz, vp, vp, vp, i, vp]
     L.mira_fft.argtypes = [i, vp, C.c_uint32, vp, i, vp]

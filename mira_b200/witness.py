@@ -200,6 +200,23 @@ class GraphEvaluator:
             pass
 
 
+def evaluate_rows_multi(programs: Sequence["GraphEvaluator"], domain: PlonkEvalDomain, outs=None, stream=None, rows=None):
+    """All cross terms of a fold in one launch (`mira_eval_rows_multi`): the programs are merged by value numbering so
+    that sub-products shared between terms are computed once per row.  Returns one tensor per program, each
+    bit-identical to `program.evaluate_rows(domain)`."""
+    import torch
+    dev = domain.device()
+    begin, end = (0, domain.row_size) if rows is None else rows
+    count = max(end - begin, 0)
+    if outs is None:
+        outs = [torch.empty(max(count, 1) * ELEM, dtype=torch.uint8, device=f"cuda:{dev}") for _ in programs]
+    d, keep = domain._struct()
+    ph = (C.c_void_p * len(programs))(*[p._h.value for p in programs])
+    po = (C.c_void_p * len(programs))(*[o.data_ptr() for o in outs])
+    _check(N.lib().mira_eval_rows_multi(ph, len(programs), C.byref(d), begin, end, po, dev, _stream(stream)))
+    return [o[: count * ELEM] for o in outs]
+
+
 # ------------------------------------------------------------------------------------------- lookup argument
 def evaluate_m(field: int, l, t, out=None, stream=None):
     """`Arguments::evaluate_m` (src/plonk/lookup.rs:278-305): multiplicity of every table value among the lookup

@@ -41,29 +41,37 @@ def _host_domain(d: Domain):
     return dom, keep
 
 
-def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
+def link_and_simulate_multi(ges, d: Domain):
+    """Links the programs (one merged device program), simulates it row by row; returns (rc, [outputs per program], stats)."""
     from mira_b200 import _native as N
     L = N.lib()
-    p = pack_program(ge)
-    h = C.c_void_p()
-    code = (C.c_uint32 * max(len(p["code"]), 1))(*p["code"])
-    rots = (C.c_int32 * max(len(p["rotations"]), 1))(*p["rotations"])
-    assert L.mira_eval_program_create(N.MIRA_FR, code, len(p["code"]), p["constants"], len(p["constants"]) // 32, rots,
-                                      len(p["rotations"]), p["num_intermediates"], C.byref(h)) == 0
+    handles = []
+    for ge in ges:
+        p = pack_program(ge)
+        h = C.c_void_p()
+        code = (C.c_uint32 * max(len(p["code"]), 1))(*p["code"])
+        rots = (C.c_int32 * max(len(p["rotations"]), 1))(*p["rotations"])
+        assert L.mira_eval_program_create(N.MIRA_FR, code, len(p["code"]), p["constants"], len(p["constants"]) // 32, rots,
+                                          len(p["rotations"]), p["num_intermediates"], C.byref(h)) == 0
+        handles.append(h)
     dom, keep = _host_domain(d)
-    cap = 4096
+    cap = 8192
     iw = (C.c_uint32 * (4 * cap))()
     aw = (C.c_uint64 * (3 * cap))()
-    ni, na = C.c_size_t(), C.c_size_t()
-    rk, ri, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
-    rc = L.mira_test_eval_link(h, C.byref(dom), iw, cap, C.byref(ni), aw, cap, C.byref(na), C.byref(rk), C.byref(ri), C.byref(ns))
-    if rc:
-        L.mira_eval_program_destroy(h)
-        return rc, None, None
+    ub = C.create_string_buffer(32 * cap)
+    ni, na, nu = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    ns = C.c_uint32()
+    ph = (C.c_void_p * len(handles))(*[h.value for h in handles])
+    rc = L.mira_test_eval_link_multi(ph, len(handles), C.byref(dom), iw, cap, C.byref(ni), aw, cap, C.byref(na), ub, cap, C.byref(nu),
+                                     C.byref(ns))
     st = N.EvalStats()
-    L.mira_eval_program_stats(h, C.byref(st))
-    L.mira_eval_program_destroy(h)
-    uniforms = unmont(p["constants"], M) + list(d.challenges) + [0]
+    if not rc:
+        L.mira_eval_program_stats(handles[0], C.byref(st))
+    for h in handles:
+        L.mira_eval_program_destroy(h)
+    if rc:
+        return rc, None, None
+    uniforms = unmont(ub.raw[: 32 * nu.value], M)
     rows = d.row_size
 
     def fetch(kind, idx, slots, row):
@@ -78,19 +86,23 @@ def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
             return 1 if C.string_at(ptr + r, 1)[0] else 0
         return R.from_mont_bytes(C.string_at(ptr + 32 * r, 32), M)
 
-    out = []
+    outs = [[None] * rows for _ in ges]
     for row in range(rows):
         slots = [None] * max(ns.value, 1)
         for k in range(ni.value):
             w0, a, b, w3 = iw[4 * k], iw[4 * k + 1], iw[4 * k + 2], iw[4 * k + 3]
             op, ak, bk, dst = w0 & 0xf, (w0 >> 4) & 0xf, (w0 >> 8) & 0xf, w0 >> 16
-            assert dst < ns.value
             x = fetch(ak, a, slots, row)
-            if op >= 7:                                  # fused a*b +- c*d
+            if op == 9:                                  # out[dst] = a
+                assert outs[dst][row] is None
+                outs[dst][row] = x % M
+                continue
+            assert dst < ns.value
+            if op in (7, 8):                             # fused a*b +- c*d
                 y = fetch(bk, b, slots, row)
                 c = fetch((w3 >> 14) & 3, w3 & 0x3fff, slots, row)
-                d = fetch(w3 >> 30, (w3 >> 16) & 0x3fff, slots, row)
-                v = x * y + c * d if op == 7 else x * y - c * d
+                dd = fetch(w3 >> 30, (w3 >> 16) & 0x3fff, slots, row)
+                v = x * y + c * dd if op == 7 else x * y - c * dd
             elif op <= 2:
                 y = fetch(bk, b, slots, row)
                 v = (x + y) if op == 0 else (x - y) if op == 1 else x * y
@@ -99,9 +111,14 @@ def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
             elif op == 5: v = -x
             else: v = x
             slots[dst] = v % M
-        out.append(fetch(rk.value, ri.value, slots, row))
-    return 0, out, {"instructions": ni.value, "slots": ns.value, "accesses": na.value, "muls": st.muls, "adds": st.adds, "loads": st.loads,
-                    "fused": st.fused}
+    assert all(v is not None for o in outs for v in o)
+    return 0, outs, {"instructions": st.instructions, "slots": ns.value, "accesses": na.value, "muls": st.muls, "adds": st.adds,
+                     "loads": st.loads, "fused": st.fused, "device_words": ni.value}
+
+
+def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
+    rc, outs, st = link_and_simulate_multi([ge], d)
+    return rc, (outs[0] if outs else None), st
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -190,3 +207,40 @@ def test_linker_reports_the_reference_errors():
     bad.calculations = [((G.OP_ADD, (G.VS_CONSTANT, 99, 0), (G.VS_CONSTANT, 0, 0)), 0)]
     bad.num_intermediates = 1
     assert link_and_simulate(bad, d)[0] == N.MIRA_ERR_EVAL_PROGRAM
+
+
+@pytest.mark.parametrize("T,n_gates", [(5, 1), (5, 2)])
+def test_merged_cross_terms_share_subproducts_and_match(T, n_gates):
+    """mira_eval_rows_multi's linker: all cross terms of a circuit as ONE program.  Every output equals the oracle's
+    evaluation of its own program, and value numbering removes the products the terms have in common."""
+    progs, meta = G.cross_term_programs(T, n_gates, M)
+    d = Domain(M, 3, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=57, sparse=True)
+    rc, outs, st = link_and_simulate_multi(progs, d)
+    assert rc == 0
+    for p, o in zip(progs, outs):
+        assert o == unmont(O.eval_rows(R.FR, pack_program(p), d.as_bytes()), M)
+    separate = sum(p.counts()["mul"] for p in progs)
+    assert st["muls"] < 0.6 * separate, (st, separate)           # 431 -> ~225, 1306 -> ~487
+    assert st["slots"] <= 256
+
+
+def test_merged_programs_with_distinct_constants_and_a_constant_output():
+    d = Domain(M, 4, 1, 2, 2, 0, 1, 2, seed=58)
+    rng = random.Random(59)
+    exprs = [random_expr(rng, M, 1 + 2 + 4, 2, depth=6, rotations=(0, 1, -2)) for _ in range(5)]
+    exprs.append(G.Constant(77))                                    # an output that is a uniform
+    exprs.append(exprs[0])                                          # the same program twice
+    ges = [G.GraphEvaluator.new(e, M) for e in exprs]
+    rc, outs, st = link_and_simulate_multi(ges, d)
+    assert rc == 0
+    for e, o in zip(exprs, outs):
+        assert o == d.direct(e, range(4))
+    # programs that re-assign a target cannot be merged
+    from mira_b200 import _native as N
+    bad = G.GraphEvaluator(M)
+    bad.rotations = [0]
+    bad.calculations = [((G.OP_MUL, (G.VS_POLY, 1, 0), (G.VS_POLY, 2, 0)), 0), ((G.OP_ADD, (G.VS_INTERMEDIATE, 0, 0), (G.VS_POLY, 1, 0)), 0)]
+    bad.num_intermediates = 1
+    assert link_and_simulate_multi([ges[0], bad], d)[0] == N.MIRA_ERR_EVAL_PROGRAM
+    rc, outs, _ = link_and_simulate_multi([bad], d)                # ... but still work alone
+    assert rc == 0 and outs[0] == [(d.column(1, r) * d.column(2, r) + d.column(1, r)) % M for r in range(4)]

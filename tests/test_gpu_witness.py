@@ -394,3 +394,24 @@ def test_sps_round_with_lookup_end_to_end(W):
     torch.cuda.synchronize()
     assert host(w3_g) == O.concat_pad([h_o, g_o], rows)
     assert ck.commit_device(w3_g.data_ptr(), 2 * rows) == O.commit(R.BN254, bases[:64 * 2 * rows], O.concat_pad([h_o, g_o], rows))
+
+
+@pytest.mark.parametrize("T,n_gates", [(5, 1), (5, 2)])
+def test_merged_cross_terms_equal_separate_evaluation(W, T, n_gates):
+    """mira_eval_rows_multi: all cross terms in one launch, shared sub-products computed once — every output is
+    bit-identical to the oracle's evaluation of its own program, also on a row range."""
+    progs, meta = G.cross_term_programs(T, n_gates, M)
+    rows = 1 << 10
+    d = Domain(M, rows, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=91 + n_gates, sparse=True)
+    gd = gpu_domain(W, d)
+    db = d.as_bytes()
+    packed = [pack_program(p) for p in progs]
+    gp = [W.GraphEvaluator(FR, p["code"], p["constants"], p["rotations"], p["num_intermediates"]) for p in packed]
+    want = [O.eval_rows(FR, p, db) for p in packed]
+    got = W.evaluate_rows_multi(gp, gd)
+    assert [host(g) for g in got] == want
+    st = gp[0].stats()
+    assert st["muls"] < 0.6 * sum(p.counts()["mul"] for p in progs)
+    part = W.evaluate_rows_multi(gp, gd, rows=(100, 357))
+    assert [host(g) for g in part] == [w[32 * 100:32 * 357] for w in want]
+    assert host(gp[2].evaluate_rows(gd)) == want[2]                 # a program still evaluates alone afterwards

@@ -100,8 +100,11 @@ class GpuFoldStep:
                 ck = st["ck"]
                 commits.append(ck.commit_device(st["W2"].data_ptr(), s["n_w"], sh))
                 dom = W.PlonkEvalDomain(s["meta"]["num_advice"], 0, st["ch"], [], st["fixed"], [st["W1"]], [st["W2"]])
-                for prog, t in zip(st["progs"], st["T"]):
-                    prog.evaluate_rows(dom, out=t, stream=sh)
+                if self.batch:      # all cross terms in one launch, shared sub-products computed once
+                    W.evaluate_rows_multi(st["progs"], dom, outs=st["T"], stream=sh)
+                else:
+                    for prog, t in zip(st["progs"], st["T"]):
+                        prog.evaluate_rows(dom, out=t, stream=sh)
                 if self.batch:      # all cross-term commitments of the fold in one call
                     commits += ck.commit_batch_device([t.data_ptr() for t in st["T"]], s["rows"], sh)
                 else:
