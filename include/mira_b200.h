@@ -66,6 +66,11 @@ int mira_msm_ctx_prepare(mira_msm_ctx *ctx, size_t n);
  * n > len  => MIRA_ERR_TOO_LONG_INPUT, nothing written (checked before any arithmetic, as upstream).
  * `scalars` is a HOST pointer; the host->device copy is part of the call. */
 int mira_msm_commit(mira_msm_ctx *ctx, const void *scalars, size_t n, void *out_affine);
+/* The device copy of the scalars of the LAST successful mira_msm_commit / host-scalar mira_msm_partial on this context
+ * (*n_out elements; NULL if none).  It stays valid until the next host-buffer commit on the context, so a caller that
+ * committed a witness from host memory can feed the same bytes to mira_eval_rows* / mira_fold_w without a second
+ * H2D copy (run_sps_protocol then commit_cross_terms then fold, src/nifs/vanilla/mod.rs:220-251). */
+const void *mira_msm_scalars_device(const mira_msm_ctx *ctx, size_t *n_out);
 /* Same, with `scalars` already resident on the context's device (e.g. produced by the cross-term
  * kernels); `stream` is a cudaStream_t (NULL = the context's own stream).  The result is still
  * returned to the host because every caller hashes it (src/poseidon/poseidon_hash.rs:129-143). */

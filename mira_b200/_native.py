@@ -26,13 +26,13 @@ MIRA_EVAL_LOOKUP_DOMAIN = 1
 # every symbol include/mira_b200.h declares (tests/test_capi_symbols.py checks the .so exports them all)
 SYMBOLS = [
     "mira_last_error", "mira_msm_ctx_create", "mira_msm_ctx_destroy", "mira_msm_ctx_len",
-    "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_commit", "mira_msm_commit_device", "mira_msm_commit_batch",
+    "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_commit", "mira_msm_commit_device", "mira_msm_commit_batch", "mira_msm_scalars_device",
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_msm_set_slice_min", "mira_host_register", "mira_host_unregister", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
     "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_lookup_m", "mira_lookup_h_g", "mira_fft", "mira_fft_std", "mira_test_eval_link_multi", "mira_eval_rows_multi",
 ]
-_VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy")
+_VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy", "mira_msm_scalars_device")
 
 
 class EvalDomain(C.Structure):
@@ -86,6 +86,8 @@ def lib():
     L.mira_msm_ctx_prepare.argtypes = [vp, sz]
     L.mira_msm_commit.argtypes = [vp, vp, sz, vp]
     L.mira_msm_commit_device.argtypes = [vp, vp, sz, vp, vp]
+    L.mira_msm_scalars_device.argtypes = [vp, C.POINTER(sz)]
+    L.mira_msm_scalars_device.restype = vp
     L.mira_msm_commit_batch.argtypes = [vp, vp, sz, sz, vp, vp]
     L.mira_msm_partial.argtypes = [vp, vp, sz, i, vp, vp]
     L.mira_msm_combine.argtypes = [i, vp, sz, i, vp]

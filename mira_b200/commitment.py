@@ -167,6 +167,19 @@ class CommitmentKey:
         _check(N.lib().mira_msm_commit_device(self._ctx, scalars_dev_ptr, n, out, stream or None), n, self._n)
         return out.raw
 
+    def scalars_device(self):
+        """Device copy of the scalars of the last host-buffer commit, as a CUDA uint8 tensor view (no copy); None if
+        there is none.  Valid until the next host-buffer commit on this key."""
+        import torch
+        n = C.c_size_t(0)
+        ptr = N.lib().mira_msm_scalars_device(self._ctx, C.byref(n))
+        if not ptr or not n.value:
+            return None
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n.value * SCALAR_BYTES,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_View(), device=f"cuda:{self.device}")
+
     def commit_batch_device(self, scalar_dev_ptrs, n: int, stream: int = 0):
         """`vs.iter().map(|v| ck.commit(v))` for device vectors of equal length n in one call (one sort, one
         accumulation, one reduction for all of them).  Returns a list of 64-byte commitments."""

@@ -69,6 +69,7 @@ struct mira_msm_ctx {
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
+  size_t scalars_valid = 0;                    // scalars.p holds the device copy of the last host-buffer commit (this many)
   void* h_result = nullptr;  // pinned, 4 KiB (up to 32 affine results of a batched commit)
   int forced_window = 0;
   size_t slice_min = (size_t)1 << 19;          // host-buffer commits: smallest (first) slice of the geometric H2D pipeline

@@ -174,6 +174,12 @@ int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
   return MIRA_OK;
 }
 
+const void* mira_msm_scalars_device(const mira_msm_ctx* ctx, size_t* n_out) {
+  if (!ctx) return nullptr;
+  if (n_out) *n_out = ctx->scalars_valid;
+  return ctx->scalars_valid ? ctx->scalars.p : nullptr;
+}
+
 int mira_host_register(void* host_ptr, size_t bytes) {
   if (!host_ptr || !bytes) return fail(MIRA_ERR_INVALID, "null argument");
   cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);

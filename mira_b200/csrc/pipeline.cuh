@@ -266,6 +266,7 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
     ctx->stats = mira_msm_stats{};
     return MIRA_OK;
   }
+  ctx->scalars_valid = 0;
   if ((rc = ctx->scalars.ensure(n * 32))) return rc;
   // Slice sizes grow geometrically (1 : 4 : 16 : 64): accumulating a slice takes ~4x as long as copying it, so every
   // copy but the first hides behind the previous slice's compute and the exposed first copy is as small as
@@ -331,6 +332,7 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
     const void* sets[1] = {(const char*)ctx->scalars.p + first * 32};
     if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, first, cnt, k > 0, st, nullptr))) return rc;
   }
+  ctx->scalars_valid = n;
   return msm_finish<CF>(ctx, &plan, st, nullptr);
 }
 

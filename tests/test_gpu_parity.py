@@ -319,3 +319,21 @@ def test_batched_commit_equals_individual_commits(gpu, curve):
     with pytest.raises(TooLongInput):
         ck.commit_batch_device([devs[0].data_ptr()], n + 1)
     assert ck.commit(vecs[0]) == want[0]                           # the single-vector path still works afterwards
+
+
+def test_device_copy_of_host_scalars_is_reusable(gpu):
+    """mira_msm_scalars_device: the device copy a host-buffer commit made (sliced or staged from pageable memory) holds
+    exactly the caller's bytes, so evaluation and fold can reuse it without a second H2D."""
+    from mira_b200 import BN254_G1, CommitmentKey
+    n = 30_011
+    bases = O.gen_bases(R.BN254, 51, n)
+    sc = O.gen_scalars(R.BN254, 52, n, 1)
+    ck = CommitmentKey(BN254_G1, bases)
+    assert ck.scalars_device() is None
+    ck.set_slice_min(500)
+    want = ck.commit(sc)                                   # pageable bytes object: staged path, 4 slices
+    view = ck.scalars_device()
+    assert gpu.to_bytes(view) == sc
+    assert ck.commit_device(view.data_ptr(), n) == want == O.commit(R.BN254, bases, sc)
+    pinned = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
+    assert ck.commit(pinned) == want and gpu.to_bytes(ck.scalars_device()) == sc

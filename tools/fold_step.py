@@ -95,11 +95,16 @@ class GpuFoldStep:
         sh = self.stream.cuda_stream
         with torch.cuda.stream(self.stream):
             for s, st in zip(self.sh, self.state):
-                if from_host:
-                    st["W2"].copy_(st["W2_host"], non_blocking=True)
                 ck = st["ck"]
-                commits.append(ck.commit_device(st["W2"].data_ptr(), s["n_w"], sh))
-                dom = W.PlonkEvalDomain(s["meta"]["num_advice"], 0, st["ch"], [], st["fixed"], [st["W1"]], [st["W2"]])
+                if from_host:
+                    # the witness arrives in (pinned) host memory: the commit pipelines its H2D behind the accumulation,
+                    # and evaluation / fold then read the commit's own device copy — W2 crosses PCIe once
+                    commits.append(ck.commit(st["W2_host"]))
+                    w2 = ck.scalars_device()
+                else:
+                    w2 = st["W2"]
+                    commits.append(ck.commit_device(w2.data_ptr(), s["n_w"], sh))
+                dom = W.PlonkEvalDomain(s["meta"]["num_advice"], 0, st["ch"], [], st["fixed"], [st["W1"]], [w2])
                 if self.batch:      # all cross terms in one launch, shared sub-products computed once
                     W.evaluate_rows_multi(st["progs"], dom, outs=st["T"], stream=sh)
                 else:
@@ -109,7 +114,7 @@ class GpuFoldStep:
                     commits += ck.commit_batch_device([t.data_ptr() for t in st["T"]], s["rows"], sh)
                 else:
                     commits += [ck.commit_device(t.data_ptr(), s["rows"], sh) for t in st["T"]]
-                W.fold_w(s["field"], st["W1"], st["W2"], st["r"], out=st["W_out"], stream=sh)
+                W.fold_w(s["field"], st["W1"], w2, st["r"], out=st["W_out"], stream=sh)
                 W.fold_e(s["field"], st["E"], st["T"], st["r"], out=st["E_out"], stream=sh)
         return commits
 
