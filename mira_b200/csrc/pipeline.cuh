@@ -316,7 +316,7 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   if (!pageable)
     for (int k = 0; k < n_slices; k++) {
       size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
-      CU(cudaMemcpyAsync((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, cudaMemcpyHostToDevice,
+      CU(cudaMemcpyAsync((char*)ctx->scalars.p + first * 32, (const char*)h_scalars + first * 32, cnt * 32, cudaMemcpyDefault,
                          ctx->copy_stream));
       CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
     }
