@@ -118,6 +118,11 @@ int mira_msm_get_stats(const mira_msm_ctx *ctx, mira_msm_stats *out);
 int mira_msm_set_profiling(mira_msm_ctx *ctx, int enabled);
 /* override the window width chosen by the size heuristic (0 = automatic). */
 int mira_msm_set_window(mira_msm_ctx *ctx, int window_bits);
+/* By default a commit of >= 2^18 scalars looks at a sample of them (8192 scalars, 64 chunks spread over the vector)
+ * and picks the window width from the pair count the sample predicts: witness vectors are mostly zeros and small
+ * values and want a much narrower window than uniform scalars.  0 = always use the size-only heuristic.  The result
+ * never depends on the window. */
+int mira_msm_set_adaptive_window(mira_msm_ctx *ctx, int enabled);
 /* Host-buffer commits (mira_msm_commit, mira_msm_partial with host scalars) are pipelined: the vector is cut
  * into up to 4 slices of geometrically growing size (1 : 4 : 16 : 64), the smallest of at least
  * `min_scalars_per_slice` scalars (default 2^19), and slice k+1 crosses PCIe while slice k is accumulated into

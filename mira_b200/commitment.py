@@ -211,6 +211,10 @@ class CommitmentKey:
     def set_window(self, c: int):
         _check(N.lib().mira_msm_set_window(self._ctx, c))
 
+    def set_adaptive_window(self, on: bool):
+        """Window picked from a sample of the scalars (default) or from the vector length alone."""
+        _check(N.lib().mira_msm_set_adaptive_window(self._ctx, 1 if on else 0))
+
     def set_slice_min(self, n: int):
         """Host-buffer commits are pipelined in up to 4 slices of >= n scalars behind their H2D copies (0: off)."""
         _check(N.lib().mira_msm_set_slice_min(self._ctx, n))

@@ -53,6 +53,7 @@ struct Table {
 
 inline int windows_for(int c) { return (255 + c - 1) / c; }
 int choose_window(size_t n);
+int choose_window_sampled(size_t n, const uint32_t* bitlen_hist, size_t samples, double* costs /* [25], may be null */);
 
 }  // namespace mira_host
 
@@ -72,6 +73,9 @@ struct mira_msm_ctx {
   size_t scalars_valid = 0;                    // scalars.p holds the device copy of the last host-buffer commit (this many)
   void* h_result = nullptr;  // pinned, 4 KiB (up to 32 affine results of a batched commit)
   int forced_window = 0;
+  bool adaptive_window = true;                 // pick the window from a sample of the scalars (sparse witnesses want a narrow one)
+  mira_host::DevBuf sample;                    // sampled scalars + bit-length histogram
+  uint32_t* h_hist = nullptr;                  // pinned, 260 u32
   size_t slice_min = (size_t)1 << 19;          // host-buffer commits: smallest (first) slice of the geometric H2D pipeline
   bool profiling = false;
   mira_msm_stats stats{};

@@ -115,6 +115,30 @@ __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ 
   }
 }
 
+// Bit-length histogram of a SAMPLE of the scalars (n_chunks chunks of chunk_len consecutive scalars, `stride` apart):
+// hist[L] += 1 for every sampled scalar whose canonical value has bit length L (0 for zero).  Feeds
+// choose_window_sampled.  `src_stride` = distance between chunks in the source, in scalars.
+template <class SF>
+__global__ void __launch_bounds__(256) k_bitlen_hist(const void* __restrict__ scalars, uint32_t n_chunks, uint32_t chunk_len,
+                                                     size_t src_stride, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[257];
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_chunks * chunk_len) {
+    size_t idx = (size_t)(t / chunk_len) * src_stride + (t % chunk_len);
+    Fe<SF> s = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + idx * 32));
+    int L = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--)
+      if (L == 0 && s.v[k]) L = 32 * k + 32 - __clz(s.v[k]);
+    atomicAdd(&sh[L], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 257; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
 // ------------------------------------------------------------------ accumulate
 // Sorted non-zero entries occupy [0, n_sorted).  Thread t owns entries [t*L, (t+1)*L): every thread
 // does the same number of mixed adds whatever the bucket-size distribution is.  A run (maximal

@@ -87,6 +87,43 @@ struct PhaseTimer {
 //   msm_slice   digits -> sort -> accumulate for scalars [first, first + n_slice); add_mode folds into the buckets
 //   msm_finish  bucket reduction; leaves the XYZZ sum (128 B) in ctx->result.p
 constexpr int MAX_BATCH = 32;
+// Window width for this vector: from a sample of the scalars when the vector is long enough for the choice to matter.
+// `scalars` is a device pointer (on_device) or a host pointer; 64 chunks of 128 scalars spread over the vector are
+// examined (host: 64 small H2D copies of 4 KiB).  Costs ~30 us (device) / ~0.2 ms (host) including the round trip.
+constexpr size_t ADAPT_MIN_N = (size_t)1 << 18;
+constexpr uint32_t ADAPT_CHUNKS = 64, ADAPT_CHUNK_LEN = 128;
+template <class SF>
+int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device, cudaStream_t st, int* window) {
+  *window = 0;
+  if (ctx->forced_window || !ctx->adaptive_window || n < ADAPT_MIN_N) return MIRA_OK;
+  int rc;
+  const size_t samples = (size_t)ADAPT_CHUNKS * ADAPT_CHUNK_LEN, stride = n / ADAPT_CHUNKS;
+  if ((rc = ctx->sample.ensure(samples * 32 + 260 * 4))) return rc;
+  uint32_t* d_hist = (uint32_t*)((char*)ctx->sample.p + samples * 32);
+  CU(cudaMemsetAsync(d_hist, 0, 260 * 4, st));
+  const void* src = scalars;
+  size_t src_stride = stride;
+  if (!on_device) {
+    for (uint32_t k = 0; k < ADAPT_CHUNKS; k++)
+      CU(cudaMemcpyAsync((char*)ctx->sample.p + (size_t)k * ADAPT_CHUNK_LEN * 32, (const char*)scalars + (size_t)k * stride * 32,
+                         ADAPT_CHUNK_LEN * 32, cudaMemcpyDefault, st));
+    src = ctx->sample.p;
+    src_stride = ADAPT_CHUNK_LEN;
+  }
+  k_bitlen_hist<SF><<<(unsigned)((samples + 255) / 256), 256, 0, st>>>(src, ADAPT_CHUNKS, ADAPT_CHUNK_LEN, src_stride, d_hist);
+  CU(cudaMemcpyAsync(ctx->h_hist, d_hist, 257 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  double costs[25];
+  int best = choose_window_sampled(n, ctx->h_hist, samples, costs);
+  // hysteresis: a table costs seconds and gigabytes to build, so a window that already has one covering n is kept
+  // unless the sample says it is clearly (> 5 %) worse
+  int keep = 0;
+  for (auto& t : ctx->tables)
+    if (t.c >= 6 && t.c <= 24 && t.n_cover >= n && costs[t.c] <= 1.05 * costs[best] && (!keep || costs[t.c] < costs[keep])) keep = t.c;
+  *window = keep ? keep : best;
+  return MIRA_OK;
+}
+
 struct MsmPlan {
   int c = 0, W = 0;
   Table* tab = nullptr;
@@ -98,9 +135,9 @@ struct MsmPlan {
 };
 
 template <class CF>
-int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan, int n_sets = 1) {
+int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan, int n_sets = 1, int window = 0) {
   int rc;
-  int c = ctx->forced_window ? ctx->forced_window : choose_window(n);
+  int c = ctx->forced_window ? ctx->forced_window : (window ? window : choose_window(n));
   Table* tab = nullptr;
   if ((rc = get_table<CF>(ctx, c, n, &tab))) return rc;
   const int W = tab->W;
@@ -236,8 +273,10 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
     return MIRA_OK;
   }
   MsmPlan plan;
+  int window = 0;
+  if ((rc = pick_window<SF>(ctx, d_scalars, n, true, st, &window))) return rc;
   PhaseTimer pt(ctx->profiling, st);
-  if ((rc = msm_begin<CF>(ctx, n, n, st, &plan))) return rc;
+  if ((rc = msm_begin<CF>(ctx, n, n, st, &plan, 1, window))) return rc;
   const void* sets[1] = {d_scalars};
   if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, 0, n, false, st, &pt))) return rc;
   if ((rc = msm_finish<CF>(ctx, &plan, st, &pt))) return rc;
@@ -308,6 +347,8 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   // page-locked source: all copies are queued now and run by the copy engine on their own;
   // pageable source (a plain Rust Vec): each slice is staged through page-locked slots by worker threads right
   // before its compute is queued, so the staging of slice k+1 overlaps the accumulation of slice k
+  int window = 0;        // sampled BEFORE the slice copies are queued: its 64 small copies must not wait behind them
+  if ((rc = pick_window<SF>(ctx, h_scalars, n, false, st, &window))) return rc;
   cudaPointerAttributes attr{};
   bool pageable = true;
   if (cudaPointerGetAttributes(&attr, h_scalars) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
@@ -321,7 +362,7 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
       CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
     }
   MsmPlan plan;
-  if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan))) return rc;
+  if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan, 1, window))) return rc;
   for (int k = 0; k < n_slices; k++) {
     size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
     if (pageable) {

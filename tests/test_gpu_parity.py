@@ -337,3 +337,27 @@ def test_device_copy_of_host_scalars_is_reusable(gpu):
     assert ck.commit_device(view.data_ptr(), n) == want == O.commit(R.BN254, bases, sc)
     pinned = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
     assert ck.commit(pinned) == want and gpu.to_bytes(ck.scalars_device()) == sc
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_adaptive_window_only_changes_speed(gpu, curve):
+    """Commits of >= 2^18 scalars pick their window from a sample of the scalars (witness-like vectors get a much
+    narrower one than uniform vectors); the commitment must not depend on it, from device or host memory."""
+    from mira_b200 import CommitmentKey
+    n = (1 << 18) + 5
+    bases = gpu.gen_bases_dev(curve, 61, n)
+    ck = CommitmentKey(curve, bases, on_device=True)
+    host_bases = gpu.to_bytes(bases)
+    seen = {}
+    for dist in (0, 1):
+        sc = gpu.gen_scalars_dev(curve, 62 + dist, n, dist)
+        host_sc = gpu.to_bytes(sc)
+        want = O.commit(curve, host_bases, host_sc)
+        ck.set_adaptive_window(True)
+        assert ck.commit_device(sc.data_ptr(), n) == want
+        seen[dist] = ck.stats()["window_bits"]
+        assert ck.commit(host_sc) == want                      # host path samples through 64 small copies
+        ck.set_adaptive_window(False)
+        assert ck.commit_device(sc.data_ptr(), n) == want
+        default_c = ck.stats()["window_bits"]
+    assert seen[1] < seen[0] and seen[0] == default_c          # sparse -> narrower window; uniform -> the size heuristic's
