@@ -292,9 +292,9 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
 }
 
 // Scalars in HOST memory: the vector is cut into slices; slice k+1 crosses PCIe on the copy stream while slice k
-// runs digits -> sort -> accumulate, so only the first slice's copy is exposed.  (Pageable host memory makes
-// cudaMemcpyAsync synchronous, which degrades this to copy-then-compute; pinned buffers get the overlap.)
-constexpr int SLICE_MAX_COUNT = 4;                 // ctx->slice_min: do not cut below that many scalars per slice
+// runs digits -> sort -> accumulate, so only the first slice's copy is exposed.  Page-locked sources are copied by
+// the copy engine directly, pageable ones are staged through page-locked slots by worker threads (stager.hpp).
+constexpr int SLICE_MAX_COUNT = 4;                 // ctx->slice_min: smallest (first) slice, in scalars
 
 template <class CF, class SF>
 int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st) {
