@@ -44,3 +44,21 @@ def test_cpp_mirror_matches_oracle_on_gpu(tmp_path):
     r = subprocess.run([exe, "3000", "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("C++ mirror ok") == 2 and "Can't commit too long input: input len: 3001, but limit is 3000" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_witness_mirror_matches_oracle_on_gpu(tmp_path):
+    """include/mira_witness.hpp (GraphEvaluator / PlonkEvalDomain / fold / fft) driven from C++ against the oracle."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import oracle_lib
+    oracle_lib.lib()
+    exe = str(tmp_path / "witness_mirror_test")
+    libdir, oradir = os.path.join(ROOT, "mira_b200"), os.path.join(ROOT, "oracle")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", oradir,
+                    os.path.join(ROOT, "tests", "cpp", "witness_mirror_test.cpp"), "-o", exe, "-L", libdir, "-lmira_b200", "-L", oradir,
+                    "-lmira_oracle", "-Xlinker", f"-rpath={libdir}", "-Xlinker", f"-rpath={oradir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "C++ witness mirror ok" in r.stdout and "EvalError" in r.stdout
