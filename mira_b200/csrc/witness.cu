@@ -846,7 +846,8 @@ static int launch_eval(const uint4* prog, uint32_t n_instr, const void* uni, con
   size_t smem = (size_t)n_instr * 16;
   if (smem > 200 * 1024) return fail(MIRA_ERR_EVAL_PROGRAM, "program of %u device instructions does not fit shared memory", n_instr);
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_eval_rows<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_eval_rows<F, S><<<grid_for(row_end - row_begin, 128, 16), 128, smem, st>>>(prog, n_instr, uni, acc, rows, row_begin, row_end, outs);
+  static const int per_sm = [] { const char* e = getenv("MIRA_EVAL_BLOCKS_PER_SM"); return e ? atoi(e) : 16; }();
+  k_eval_rows<F, S><<<grid_for(row_end - row_begin, 128, per_sm), 128, smem, st>>>(prog, n_instr, uni, acc, rows, row_begin, row_end, outs);
   CU(cudaGetLastError());
   return MIRA_OK;
 }
