@@ -191,7 +191,10 @@ enum { MIRA_EVAL_LOOKUP_DOMAIN = 1 };
 
 /* out_dev[row] = evaluator.evaluate(&domain, row) for row in [0, row_size)
  * (the `(0..row_size).into_par_iter().map(..)` of src/nifs/vanilla/mod.rs:109-116).
- * Index errors the reference raises per row are raised here once, when the program is bound to the domain. */
+ * Index errors the reference raises per row are raised here once, when the program is bound to the domain.
+ * The linked device program is cached with the program object: binding the same program(s) to the same column
+ * pointers again (a prover does that every step) only refreshes the challenges, asynchronously on `stream`.
+ * Calls that share a program object must be issued on one stream. */
 int mira_eval_rows(const mira_eval_program *prog, const mira_eval_domain *dom, void *out_dev, int device,
                    void *stream);
 /* The same for rows [row_begin, row_end) only; out_dev holds row_end - row_begin elements.  This is the row-range

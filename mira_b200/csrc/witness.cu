@@ -10,6 +10,7 @@
 //   best_fft / fft / ifft                           src/fft.rs:12-27,51-115,160-175
 // Outputs stay in HBM so they feed mira_msm_commit_device without crossing PCIe.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -368,9 +369,17 @@ struct mira_eval_program {
   std::vector<int32_t> rotations;
   uint32_t num_intermediates = 0;
   mira_eval_stats stats{};
-  // device copies of the last binding (re-used when the same domain pointers come back)
+  // device copies of the last binding (re-used when the same programs meet the same domain pointers again: a prover
+  // binds the same circuit every step, only the challenges change)
   mira_host::DevBuf d_prog, d_uniforms, d_access;
   int device = -1;
+  uint64_t serial = 0;                 // unique per created program (addresses can be re-used, serials cannot)
+  uint64_t bind_signature = 0;         // of (programs, domain layout, column pointers); 0 = nothing cached
+  uint32_t bind_slots = 0, bind_instr = 0, bind_challenge_base = 0, bind_uniforms = 0;
+  mira_eval_stats bind_stats{};
+  void* h_stage = nullptr;             // pinned staging for the asynchronous uploads
+  size_t h_stage_cap = 0;
+  cudaEvent_t stage_free = nullptr;    // the previous upload from h_stage has been consumed
 };
 
 namespace mira_host {
@@ -852,33 +861,98 @@ static int launch_eval(const uint4* prog, uint32_t n_instr, const void* uni, con
   return MIRA_OK;
 }
 
+static uint64_t fnv(uint64_t h, const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001b3ull;
+  return h;
+}
+// Everything the linked program depends on except the challenge VALUES (those only fill the uniform table).
+static uint64_t bind_signature(mira_eval_program* const* progs, size_t n_progs, const mira_eval_domain* D) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  h = fnv(h, &n_progs, sizeof n_progs);
+  for (size_t p = 0; p < n_progs; p++) {
+    h = fnv(h, &progs[p]->serial, sizeof progs[p]->serial);
+  }
+  h = fnv(h, &D->row_size, sizeof D->row_size);
+  uint32_t f[8] = {D->num_selectors, D->num_fixed, D->num_advice, D->num_lookup, D->num_challenges, D->num_w1, D->num_w2, D->flags};
+  h = fnv(h, f, sizeof f);
+  if (D->num_selectors) h = fnv(h, D->selectors, D->num_selectors * sizeof(void*));
+  if (D->num_fixed) h = fnv(h, D->fixed, D->num_fixed * sizeof(void*));
+  if (D->num_w1) { h = fnv(h, D->w1, D->num_w1 * sizeof(void*)); h = fnv(h, D->w1_len, D->num_w1 * sizeof(uint64_t)); }
+  if (D->num_w2) { h = fnv(h, D->w2, D->num_w2 * sizeof(void*)); h = fnv(h, D->w2_len, D->num_w2 * sizeof(uint64_t)); }
+  const char* e = getenv("MIRA_EVAL_FUSE");
+  uint8_t fuse = !(e && e[0] == '0');
+  h = fnv(h, &fuse, 1);
+  return h ? h : 1;
+}
+
 template <class F>
 static int eval_impl(mira_eval_program* const* progs, size_t n_progs, const mira_eval_domain* D, uint64_t row_begin, uint64_t row_end,
                      void* const* outs, cudaStream_t st) {
-  LinkedProgram lp;
-  int rc = link_programs(progs, n_progs, D, &lp);
-  if (rc) return rc;
-  for (size_t p = 0; p < n_progs; p++) progs[p]->stats = lp.stats;
-  if (row_begin >= row_end) return MIRA_OK;
+  int rc;
   mira_eval_program* P = progs[0];          // device copies of the linked program live with the first program
-  if ((rc = P->d_prog.ensure(std::max<size_t>(lp.prog.size(), 1) * 16)) || (rc = P->d_uniforms.ensure(lp.uniforms.size())) ||
-      (rc = P->d_access.ensure(std::max<size_t>(lp.access.size(), 1) * sizeof(Access))))
-    return rc;
-  // small synchronous uploads (a few KB); the row kernel itself is asynchronous on `st`
-  CU(cudaStreamSynchronize(st));
-  CU(cudaMemcpy(P->d_prog.p, lp.prog.data(), lp.prog.size() * 16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(P->d_uniforms.p, lp.uniforms.data(), lp.uniforms.size(), cudaMemcpyHostToDevice));
-  if (!lp.access.empty()) CU(cudaMemcpy(P->d_access.p, lp.access.data(), lp.access.size() * sizeof(Access), cudaMemcpyHostToDevice));
+  const uint64_t sig = bind_signature(progs, n_progs, D);
+  auto stage = [&](size_t bytes) -> int {   // pinned staging buffer, free again once the previous upload has been consumed
+    if (!P->stage_free) CU(cudaEventCreateWithFlags(&P->stage_free, cudaEventDisableTiming));
+    CU(cudaEventSynchronize(P->stage_free));
+    if (bytes > P->h_stage_cap) {
+      if (P->h_stage) cudaFreeHost(P->h_stage);
+      P->h_stage = nullptr;
+      P->h_stage_cap = 0;
+      CU(cudaMallocHost(&P->h_stage, bytes));
+      P->h_stage_cap = bytes;
+    }
+    return MIRA_OK;
+  };
+  if (sig == P->bind_signature && P->d_prog.p) {
+    // same circuit, same columns: only the challenges (a few uniforms) are refreshed, asynchronously on `st`
+    for (size_t p = 0; p < n_progs; p++) progs[p]->stats = P->bind_stats;
+    if (row_begin >= row_end) return MIRA_OK;
+    if (D->num_challenges) {
+      size_t bytes = (size_t)D->num_challenges * 32;
+      if ((rc = stage(bytes))) return rc;
+      memcpy(P->h_stage, D->challenges, bytes);
+      CU(cudaMemcpyAsync((char*)P->d_uniforms.p + (size_t)P->bind_challenge_base * 32, P->h_stage, bytes, cudaMemcpyHostToDevice, st));
+      CU(cudaEventRecord(P->stage_free, st));
+    }
+  } else {
+    LinkedProgram lp;
+    if ((rc = link_programs(progs, n_progs, D, &lp))) return rc;
+    for (size_t p = 0; p < n_progs; p++) progs[p]->stats = lp.stats;
+    if (row_begin >= row_end) return MIRA_OK;
+    const size_t b_prog = std::max<size_t>(lp.prog.size(), 1) * 16, b_uni = lp.uniforms.size(),
+                 b_acc = std::max<size_t>(lp.access.size(), 1) * sizeof(Access);
+    P->bind_signature = 0;
+    // a kernel still running on another stream may read the old device program: drain before replacing it
+    if (P->d_prog.p) CU(cudaDeviceSynchronize());
+    if ((rc = P->d_prog.ensure(b_prog)) || (rc = P->d_uniforms.ensure(b_uni)) || (rc = P->d_access.ensure(b_acc))) return rc;
+    if ((rc = stage(b_prog + b_uni + b_acc))) return rc;
+    char* h = (char*)P->h_stage;
+    memcpy(h, lp.prog.data(), lp.prog.size() * 16);
+    memcpy(h + b_prog, lp.uniforms.data(), b_uni);
+    if (!lp.access.empty()) memcpy(h + b_prog + b_uni, lp.access.data(), lp.access.size() * sizeof(Access));
+    CU(cudaMemcpyAsync(P->d_prog.p, h, b_prog, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(P->d_uniforms.p, h + b_prog, b_uni, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(P->d_access.p, h + b_prog + b_uni, b_acc, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(P->stage_free, st));
+    P->bind_slots = lp.slots;
+    P->bind_instr = (uint32_t)lp.prog.size();
+    P->bind_uniforms = (uint32_t)(b_uni / 32);
+    P->bind_challenge_base = P->bind_uniforms - 1 - D->num_challenges;     // constants | challenges | ZERO
+    P->bind_stats = lp.stats;
+    P->bind_signature = sig;
+  }
   EvalOuts eo{};
   for (size_t p = 0; p < n_progs; p++) eo.p[p] = outs[p];
   const uint4* dp = (const uint4*)P->d_prog.p;
   const Access* da = (const Access*)P->d_access.p;
-  uint32_t ni = (uint32_t)lp.prog.size();
-  if (lp.slots <= 16) return launch_eval<F, 16>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
-  if (lp.slots <= 64) return launch_eval<F, 64>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
-  if (lp.slots <= 128) return launch_eval<F, 128>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
-  if (lp.slots <= 256) return launch_eval<F, 256>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
-  return fail(MIRA_ERR_EVAL_PROGRAM, "program keeps %u intermediates live; the device interpreter supports 256", lp.slots);
+  const uint32_t ni = P->bind_instr, slots = P->bind_slots;
+  if (slots <= 16) return launch_eval<F, 16>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
+  if (slots <= 64) return launch_eval<F, 64>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
+  if (slots <= 128) return launch_eval<F, 128>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
+  if (slots <= 256) return launch_eval<F, 256>(dp, ni, P->d_uniforms.p, da, D->row_size, row_begin, row_end, eo, st);
+  P->bind_signature = 0;
+  return fail(MIRA_ERR_EVAL_PROGRAM, "program keeps %u intermediates live; the device interpreter supports 256", slots);
 }
 
 // ---- FFT -------------------------------------------------------------------------------------------
@@ -988,7 +1062,9 @@ int mira_eval_program_create(int field, const uint32_t* code, size_t code_words,
   *out = nullptr;
   if (!valid_field(field)) return fail(MIRA_ERR_INVALID, "unknown field %d", field);
   if ((code_words && !code) || (n_constants && !constants) || (n_rotations && !rotations)) return fail(MIRA_ERR_INVALID, "null argument");
+  static std::atomic<uint64_t> next_serial{1};
   auto* p = new mira_eval_program();
+  p->serial = next_serial.fetch_add(1);
   p->field = field;
   p->code.assign(code, code + code_words);
   p->constants.assign((const uint8_t*)constants, (const uint8_t*)constants + n_constants * 32);
@@ -1004,6 +1080,8 @@ void mira_eval_program_destroy(mira_eval_program* p) {
   p->d_prog.release();
   p->d_uniforms.release();
   p->d_access.release();
+  if (p->h_stage) cudaFreeHost(p->h_stage);
+  if (p->stage_free) cudaEventDestroy(p->stage_free);
   delete p;
 }
 
@@ -1045,6 +1123,7 @@ int mira_eval_rows_multi(const mira_eval_program* const* progs, size_t n_progs, 
   if (p0->device >= 0 && p0->device != device) {
     cudaSetDevice(p0->device);
     p0->d_prog.release(); p0->d_uniforms.release(); p0->d_access.release();
+    p0->bind_signature = 0;
     cudaSetDevice(device);
   }
   p0->device = device;

@@ -415,3 +415,28 @@ def test_merged_cross_terms_equal_separate_evaluation(W, T, n_gates):
     part = W.evaluate_rows_multi(gp, gd, rows=(100, 357))
     assert [host(g) for g in part] == [w[32 * 100:32 * 357] for w in want]
     assert host(gp[2].evaluate_rows(gd)) == want[2]                 # a program still evaluates alone afterwards
+
+
+def test_binding_cache_refreshes_challenges_and_notices_new_columns(W):
+    """The linked program is cached per (programs, column pointers); a second call with other challenge VALUES must
+    use them, and a call with different column buffers must re-link."""
+    progs, meta = G.cross_term_programs(5, 1, M)
+    rows = 300
+    packed = [pack_program(p) for p in progs]
+    gp = [W.GraphEvaluator(FR, p["code"], p["constants"], p["rotations"], p["num_intermediates"]) for p in packed]
+    d1 = Domain(M, rows, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=71, sparse=True)
+    gd = gpu_domain(W, d1)
+    assert [host(g) for g in W.evaluate_rows_multi(gp, gd)] == [O.eval_rows(FR, p, d1.as_bytes()) for p in packed]
+    # same device columns, new challenges (what every fold step does)
+    d1.challenges = [(c * 7 + 3) % M for c in d1.challenges]
+    gd.challenges = mont(d1.challenges, M)
+    assert [host(g) for g in W.evaluate_rows_multi(gp, gd)] == [O.eval_rows(FR, p, d1.as_bytes()) for p in packed]
+    # new contents in the SAME buffers are picked up (columns are read at run time)
+    d1.fixed[0] = [(v + 1) % M for v in d1.fixed[0]]
+    gd.fixed[0].copy_(dev(mont(d1.fixed[0], M)))
+    assert [host(g) for g in W.evaluate_rows_multi(gp, gd)] == [O.eval_rows(FR, p, d1.as_bytes()) for p in packed]
+    # different buffers: re-link
+    d2 = Domain(M, rows, 0, meta["num_fixed"], meta["num_advice"], 0, 1, meta["num_challenges"], seed=72)
+    gd2 = gpu_domain(W, d2)
+    assert [host(g) for g in W.evaluate_rows_multi(gp, gd2)] == [O.eval_rows(FR, p, d2.as_bytes()) for p in packed]
+    assert host(gp[0].evaluate_rows(gd)) == O.eval_rows(FR, packed[0], d1.as_bytes())
