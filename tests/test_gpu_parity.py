@@ -361,3 +361,38 @@ def test_adaptive_window_only_changes_speed(gpu, curve):
         assert ck.commit_device(sc.data_ptr(), n) == want
         default_c = ck.stats()["window_bits"]
     assert seen[1] < seen[0] and seen[0] == default_c          # sparse -> narrower window; uniform -> the size heuristic's
+
+
+def test_randomized_commit_configurations(gpu):
+    """Seeded random sweep over (curve, length, distribution, window, slicing, adaptive, source) — every combination must
+    give the oracle's bytes.  60 configurations, sizes up to 40,000."""
+    from mira_b200 import CommitmentKey
+    rng = random.Random(20261018)
+    keys = {}
+    for it in range(60):
+        curve = rng.choice([R.BN254, R.GRUMPKIN])
+        n_key = rng.choice([1, 2, 33, 1000, 9973, 40_000])
+        if (curve, n_key) not in keys:
+            b = O.gen_bases(curve, 1000 + n_key, n_key)
+            keys[(curve, n_key)] = (b, CommitmentKey(curve, b))
+        bases, ck = keys[(curve, n_key)]
+        n = rng.choice([0, 1, n_key // 2, max(n_key - 1, 0), n_key])
+        dist = rng.choice([0, 1])
+        sc = O.gen_scalars(curve, 5000 + it, n, dist)
+        if n and rng.random() < 0.2:                                  # a block of identical scalars: heavy buckets
+            one = O.gen_scalars(curve, 7, 1)
+            k = rng.randrange(1, n + 1)
+            sc = one * k + sc[32 * k:]
+        ck.set_window(rng.choice([0, 0, 0, 2, 3, 7, 11, 16, 21]))
+        ck.set_slice_min(rng.choice([0, 1, 50, 1 << 19]))
+        ck.set_adaptive_window(rng.random() < 0.5)
+        want = O.commit(curve, bases, sc)
+        src = rng.choice(["bytes", "pinned", "device"])
+        if src == "bytes":
+            got = ck.commit(sc)
+        elif src == "pinned":
+            got = ck.commit(torch.frombuffer(bytearray(sc) if sc else bytearray(32), dtype=torch.uint8).pin_memory()[: len(sc)])
+        else:
+            d = torch.frombuffer(bytearray(sc) if sc else bytearray(32), dtype=torch.uint8).cuda()
+            got = ck.commit_device(d.data_ptr(), n)
+        assert got == want, (it, curve, n_key, n, dist, src, ck.stats())
