@@ -157,17 +157,31 @@ __global__ void k_fft_consts(uint32_t k, int inverse, void* consts) {
   fe_store<F>(reinterpret_cast<char*>(consts) + 32, d);
 }
 
-// tw[i] = omega^i, i < half (square-and-multiply per thread: exact, so equal to the reference's running product)
+// tw[i] = omega^(i * stride), i < count (square-and-multiply per thread: exact, so equal to the reference's running
+// product).  Used directly for small transforms and for the two small tables of the large ones.
 template <class F>
-__global__ void __launch_bounds__(256) k_fft_twiddles(const void* __restrict__ consts, size_t half, void* __restrict__ tw) {
+__global__ void __launch_bounds__(256) k_fft_twiddles(const void* __restrict__ consts, size_t count, size_t stride, void* __restrict__ tw) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= half) return;
+  if (i >= count) return;
   Fe<F> base = fe_load<F>(consts), acc = fe_one<F>();
-  for (size_t e = i; e; e >>= 1) {
+  for (size_t e = i * stride; e; e >>= 1) {
     if (e & 1) acc = fe_mul(acc, base);
     base = fe_sqr(base);
   }
   fe_store<F>(reinterpret_cast<char*>(tw) + i * 32, acc);
+}
+
+// Large tables: tw[i] = hi[i >> FFT_TW_LOW] * tw[i & (2^FFT_TW_LOW - 1)] for i >= 2^FFT_TW_LOW -- one multiplication
+// per twiddle instead of a ~2 log2(i)-multiplication power (which cost as much as the transform itself at 2^24).
+constexpr int FFT_TW_LOW = 10;
+template <class F>
+__global__ void __launch_bounds__(256) k_fft_twiddles_combine(const void* __restrict__ hi, size_t half, void* __restrict__ tw) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x + ((size_t)1 << FFT_TW_LOW);
+  if (i >= half) return;
+  const char* t = reinterpret_cast<const char*>(tw);
+  Fe<F> h = fe_load<F>(reinterpret_cast<const char*>(hi) + (i >> FFT_TW_LOW) * 32);
+  Fe<F> l = fe_load<F>(t + (i & (((size_t)1 << FFT_TW_LOW) - 1)) * 32);
+  fe_store<F>(reinterpret_cast<char*>(tw) + i * 32, fe_mul(h, l));
 }
 
 template <class F>
@@ -229,6 +243,54 @@ __global__ void __launch_bounds__(256) k_fft_stage(void* a, uint32_t log_n, uint
   if (i) r = fe_mul(r, fe_load<F>(reinterpret_cast<const char*>(tw) + (i * (n >> (s + 1))) * 32));
   fe_store<F>(p + left * 32, fe_add(l, r));
   fe_store<F>(p + right * 32, fe_sub(l, r));
+}
+
+// Stages [s0, s0 + R) fused in shared memory for the stages beyond the contiguous tile: a block takes 2^R rows that
+// are 2^s0 apart and FFT_COLS consecutive columns (8 x 32 B = 256 B contiguous per row, so the strided gather is
+// still made of full sectors), runs the R butterfly stages over the row dimension and writes back.  One HBM round
+// trip for up to 7 stages instead of one per stage.
+constexpr int FFT_COLS = 8, FFT_STRIDED_LOG = 7;
+template <class F>
+__global__ void __launch_bounds__(256) k_fft_strided(void* a, uint32_t log_n, uint32_t s0, uint32_t R, const void* __restrict__ tw) {
+  extern __shared__ uint4 sm_fft[];                       // [2^R rows][FFT_COLS] elements
+  const size_t n = (size_t)1 << log_n;
+  const uint32_t rows = 1u << R;
+  const size_t col_blocks = ((size_t)1 << s0) / FFT_COLS;
+  const size_t group = blockIdx.x / col_blocks, cb = blockIdx.x % col_blocks;
+  const size_t base = (group << (s0 + R)) | (cb * FFT_COLS);
+  char* g = reinterpret_cast<char*>(a);
+  for (uint32_t e = threadIdx.x; e < rows * FFT_COLS * 2; e += blockDim.x) {       // uint4 granularity: 2 per element
+    uint32_t el = e >> 1, row = el / FFT_COLS, c = el % FFT_COLS;
+    sm_fft[e] = reinterpret_cast<const uint4*>(g + (base + ((size_t)row << s0) + c) * 32)[e & 1];
+  }
+  __syncthreads();
+  for (uint32_t k = 0; k < R; k++) {
+    const uint32_t s = s0 + k, half = 1u << k;
+    const size_t twiddle_chunk = n >> (s + 1);
+    for (uint32_t t = threadIdx.x; t < rows / 2 * FFT_COLS; t += blockDim.x) {
+      uint32_t c = t % FFT_COLS, p = t / FFT_COLS;                                  // p-th butterfly over the rows
+      uint32_t i = p & (half - 1), left = ((p >> k) << (k + 1)) + i, right = left + half;
+      // position of the left element inside its 2^(s+1) chunk = (low k bits of the row) << s0 | column
+      size_t pos = ((size_t)i << s0) | (cb * FFT_COLS + c);
+      uint32_t li = (left * FFT_COLS + c) * 2, ri = (right * FFT_COLS + c) * 2;
+      Fe<F> l, r;
+      {
+        uint4 lo = sm_fft[li], hi = sm_fft[li + 1];
+        l.v[0] = lo.x; l.v[1] = lo.y; l.v[2] = lo.z; l.v[3] = lo.w; l.v[4] = hi.x; l.v[5] = hi.y; l.v[6] = hi.z; l.v[7] = hi.w;
+        lo = sm_fft[ri]; hi = sm_fft[ri + 1];
+        r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+      }
+      if (pos) r = fe_mul(r, fe_load<F>(reinterpret_cast<const char*>(tw) + (pos * twiddle_chunk) * 32));
+      Fe<F> x = fe_add(l, r), y = fe_sub(l, r);
+      sm_fft[li] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]); sm_fft[li + 1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+      sm_fft[ri] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]); sm_fft[ri + 1] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = threadIdx.x; e < rows * FFT_COLS * 2; e += blockDim.x) {
+    uint32_t el = e >> 1, row = el / FFT_COLS, c = el % FFT_COLS;
+    reinterpret_cast<uint4*>(g + (base + ((size_t)row << s0) + c) * 32)[e & 1] = sm_fft[e];
+  }
 }
 
 template <class F>
@@ -966,12 +1028,35 @@ static int fft_impl(void* a, uint32_t log_n, const void* d_consts, bool scale, c
   }
   void* tw = nullptr;
   CU(cudaMallocAsync(&tw, half * 32, st));
-  k_fft_twiddles<F><<<(unsigned)((half + 255) / 256), 256, 0, st>>>(d_consts, half, tw);
+  const size_t low = (size_t)1 << FFT_TW_LOW;
+  if (half <= low) {
+    k_fft_twiddles<F><<<(unsigned)((half + 255) / 256), 256, 0, st>>>(d_consts, half, 1, tw);
+  } else {
+    void* hi = nullptr;
+    if (cudaMallocAsync(&hi, (half >> FFT_TW_LOW) * 32, st) != cudaSuccess) {
+      cudaFreeAsync(tw, st);
+      return fail(MIRA_ERR_CUDA, "fft: cannot allocate the twiddle table");
+    }
+    k_fft_twiddles<F><<<(unsigned)(low / 256), 256, 0, st>>>(d_consts, low, 1, tw);
+    k_fft_twiddles<F><<<(unsigned)(((half >> FFT_TW_LOW) + 255) / 256), 256, 0, st>>>(d_consts, half >> FFT_TW_LOW, low, hi);
+    k_fft_twiddles_combine<F><<<(unsigned)((half - low + 255) / 256), 256, 0, st>>>(hi, half, tw);
+    cudaFreeAsync(hi, st);
+  }
   k_fft_bitrev<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, log_n);
   uint32_t fused = log_n < (uint32_t)FFT_TILE_LOG ? log_n : (uint32_t)FFT_TILE_LOG;
   size_t tile = (size_t)1 << fused;
   k_fft_tile<F><<<(unsigned)(n / tile), 512, tile * 32, st>>>(a, log_n, fused, tw);
-  for (uint32_t s = fused; s < log_n; s++) k_fft_stage<F><<<(unsigned)((half + 255) / 256), 256, 0, st>>>(a, log_n, s, tw);
+  // remaining stages: up to 7 per HBM round trip (strided tiles); a lone last stage goes through the per-stage kernel
+  for (uint32_t s = fused; s < log_n;) {
+    uint32_t R = log_n - s < (uint32_t)FFT_STRIDED_LOG ? log_n - s : (uint32_t)FFT_STRIDED_LOG;
+    if (R == 1) {
+      k_fft_stage<F><<<(unsigned)((half + 255) / 256), 256, 0, st>>>(a, log_n, s, tw);
+    } else {
+      size_t blocks = (n >> (s + R)) * (((size_t)1 << s) / FFT_COLS);
+      k_fft_strided<F><<<(unsigned)blocks, 256, ((size_t)1 << R) * FFT_COLS * 32, st>>>(a, log_n, s, R, tw);
+    }
+    s += R;
+  }
   if (scale) k_scale<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, reinterpret_cast<const char*>(d_consts) + 32);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(tw, st);

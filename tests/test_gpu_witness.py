@@ -272,7 +272,7 @@ def test_fft_reference_kat(W):
     assert unmont(host(a), M) == g["input"]
 
 
-@pytest.mark.parametrize("k", [0, 1, 2, 4, 5, 6, 7, 8, 10, 11, 13, 16])
+@pytest.mark.parametrize("k", [0, 1, 2, 4, 5, 6, 7, 8, 10, 11, 12, 13, 16, 18, 19])
 def test_fft_vs_oracle_and_roundtrip(W, k):
     n = 1 << k
     vals = O.gen_scalars(R.BN254, 900 + k, n, 0)
