@@ -128,6 +128,11 @@ int mira_msm_set_adaptive_window(mira_msm_ctx *ctx, int enabled);
  * `min_scalars_per_slice` scalars (default 2^19), and slice k+1 crosses PCIe while slice k is accumulated into
  * the same bucket set.  0 disables slicing.  The result does not depend on it. */
 int mira_msm_set_slice_min(mira_msm_ctx *ctx, size_t min_scalars_per_slice);
+/* Experimental, off by default (0): before the XYZZ accumulation, add the entries of every bucket two by two in
+ * AFFINE coordinates `levels` times (0..6), each level sharing its inversions by Montgomery's trick
+ * (mira_b200/csrc/affine_levels.cuh).  5M + 1S per addition instead of 8M + 2S, but two passes over the gathered
+ * points: measured neutral on B200, kept as a tested alternative.  The result does not depend on it. */
+int mira_msm_set_affine_levels(mira_msm_ctx *ctx, int levels);
 
 /* ==== field vectors in HBM: the witness side of the hot path =====
  * `field` is the SCALAR field of the curve being committed to: MIRA_FR for BN254 G1, MIRA_FQ for

@@ -219,6 +219,10 @@ class CommitmentKey:
         """Host-buffer commits are pipelined in up to 4 slices of >= n scalars behind their H2D copies (0: off)."""
         _check(N.lib().mira_msm_set_slice_min(self._ctx, n))
 
+    def set_affine_levels(self, levels: int):
+        """Experimental (default 0): batched-affine pre-reduction levels before the XYZZ accumulation."""
+        _check(N.lib().mira_msm_set_affine_levels(self._ctx, levels))
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             N.lib().mira_msm_ctx_destroy(self._ctx)

@@ -70,6 +70,8 @@ struct mira_msm_ctx {
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
+  mira_host::DevBuf pa_a, pa_b, pa_work;       // batched-affine levels (affine_levels.cuh): two ping-pong (key, point) lists, scratch
+  int affine_levels = -1;                      // -1 = MIRA_AFFINE_LEVELS from the environment (default 0 = off)
   size_t scalars_valid = 0;                    // scalars.p holds the device copy of the last host-buffer commit (this many)
   void* h_result = nullptr;  // pinned, 4 KiB (up to 32 affine results of a batched commit)
   int forced_window = 0;

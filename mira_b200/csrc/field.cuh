@@ -311,10 +311,64 @@ template <class F> __device__ __noinline__ Fe<F> fe_inv(const Fe<F>& a) {
   return fe_mul(fe_mul(r, r2), r2);
 }
 
+// The same inverse by a branch-uniform binary GCD, for code where all 32 lanes of a warp invert at once (fe_inv's
+// data-dependent inner loops would then serialise).  Loop: u even -> halve; u odd -> (swap so that u >= v), u -= v,
+// halve; v stays odd, and u = 0 leaves v = gcd = 1 with x2 = A^{-1}.  Every step is selects and carry chains.
+template <class F> __device__ __noinline__ Fe<F> fe_inv_uniform(const Fe<F>& a) {
+  if (fe_is_zero(a)) return a;
+  uint32_t u[8], v[8], x1[8], x2[8], p[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u[i] = a.v[i];
+    p[i] = v[i] = FieldParams<F>::mod(i);
+    x1[i] = (i == 0);
+    x2[i] = 0;
+  }
+  for (;;) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nz |= u[i];
+    if (!nz) break;
+    if (u[0] & 1u) {
+      if (!u256_ge(u, v)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          uint32_t t = u[i]; u[i] = v[i]; v[i] = t;
+          t = x1[i]; x1[i] = x2[i]; x2[i] = t;
+        }
+      }
+      u256_sub(u, v);
+      if (u256_sub(x1, x2)) u256_add(x1, p);
+    }
+    u256_shr1(u);
+    if (x1[0] & 1u) {
+      // (x1 + p) / 2 without losing the carry out of bit 255: p < 2^254, so x1 + p < 2^255 fits
+      u256_add(x1, p);
+    }
+    u256_shr1(x1);
+  }
+  Fe<F> r, r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.v[i] = x2[i];
+    r2.v[i] = FieldParams<F>::r2(i);
+  }
+  return fe_mul(fe_mul(r, r2), r2);
+}
+
 // ---- 128-bit vectorised global-memory access (elements are 32-byte aligned in all our buffers)
 template <class F> __device__ __forceinline__ Fe<F> fe_load(const void* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 lo = __ldg(q), hi = __ldg(q + 1);
+  Fe<F> r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+// plain (not read-only-path) load, for memory written earlier by the same kernel
+template <class F> __device__ __forceinline__ Fe<F> fe_load_plain(const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = q[0], hi = q[1];
   Fe<F> r;
   r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
   r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;

@@ -237,6 +237,13 @@ int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
   return MIRA_OK;
 }
 
+int mira_msm_set_affine_levels(mira_msm_ctx* ctx, int levels) {
+  if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  if (levels < 0 || levels > 6) return fail(MIRA_ERR_INVALID, "affine levels %d out of range [0, 6]", levels);
+  ctx->affine_levels = levels;
+  return MIRA_OK;
+}
+
 // ---------------------------------------------------------------------- generators / test hooks
 int mira_gen_scalars(int curve, uint64_t seed, size_t first, size_t n, int dist, int device, void* out_dev) {
   if (n && !out_dev) return fail(MIRA_ERR_INVALID, "null argument");

@@ -160,7 +160,9 @@ __device__ __forceinline__ Affine<CF> load_ref(const void* __restrict__ table, u
 #ifndef MIRA_ACC_MIN_BLOCKS
 #define MIRA_ACC_MIN_BLOCKS 1
 #endif
-template <class CF>
+// DIRECT: entry e's point is the e-th element of a dense affine list (`table`; the output of the batched-affine
+// levels, affine_levels.cuh) instead of the table entry named by srefs[e].
+template <class CF, bool DIRECT = false>
 __global__ void __launch_bounds__(128, MIRA_ACC_MIN_BLOCKS) k_accumulate(const uint32_t* __restrict__ skeys,
                                                     const uint32_t* __restrict__ srefs,
                                                     const uint32_t* __restrict__ n_ptr, int L,
@@ -197,12 +199,12 @@ __global__ void __launch_bounds__(128, MIRA_ACC_MIN_BLOCKS) k_accumulate(const u
       else acc = xyzz_identity<CF>();
     }
 #if MIRA_ACC_PREFETCH
-    if (e + MIRA_ACC_PREFETCH < end) {    // pull the point two adds ahead into L2: the gather is a dependent DRAM access
+    if (!DIRECT && e + MIRA_ACC_PREFETCH < end) {    // pull the point two adds ahead into L2: the gather is a dependent DRAM access
       const char* nxt = reinterpret_cast<const char*>(table) + (size_t)(srefs[e + MIRA_ACC_PREFETCH] & ~REF_NEG) * 64;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
     }
 #endif
-    Affine<CF> p = load_ref<CF>(table, srefs[e]);
+    Affine<CF> p = DIRECT ? aff_load<CF>(reinterpret_cast<const char*>(table) + e * 64) : load_ref<CF>(table, srefs[e]);
     xyzz_madd(acc, p);
   }
   {

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "ctx.hpp"
 #include "msm_kernels.cuh"
+#include "affine_levels.cuh"
 #include "testgen.cuh"
 
 namespace mira_host {
@@ -124,7 +125,22 @@ int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device
   return MIRA_OK;
 }
 
+// Batched-affine levels before the XYZZ accumulation (affine_levels.cuh): off unless asked for
+// (mira_msm_set_affine_levels, or MIRA_AFFINE_LEVELS in the environment for sweeps).  Measured on B200 at 2^24 points
+// (201 M pairs, 96 per bucket): 0 levels 32.2 ms, 3 levels 32.2 ms, 5 levels 32.3 ms — the cheaper additions
+// (0.10 vs 0.17 ns in isolation) are paid back by the second pass over the gathered points and the inversion kernels.
+constexpr int PA_MAX_LEVELS = 6;
+inline size_t pa_align(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+inline size_t pa_keys_bytes(size_t entries) { return pa_align(entries * 4); }
+inline size_t pa_list_bytes(size_t entries) { return pa_keys_bytes(entries) + entries * 64 + 256; }
+inline int affine_levels_for(const mira_msm_ctx* ctx) {
+  static const int env = [] { const char* e = getenv("MIRA_AFFINE_LEVELS"); return e ? atoi(e) : 0; }();
+  int want = ctx->affine_levels >= 0 ? ctx->affine_levels : env;
+  return want < 0 ? 0 : (want > PA_MAX_LEVELS ? PA_MAX_LEVELS : want);
+}
+
 struct MsmPlan {
+  int affine_levels = 0;
   int c = 0, W = 0;
   Table* tab = nullptr;
   uint32_t B = 0;
@@ -169,6 +185,7 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
   if (pt) pt->mark(0);
   // ---- digits (compacted pair list)
   CU(cudaMemsetAsync(d_npairs, 0, 4, st));
+  if (!add_mode) CU(cudaMemsetAsync((char*)ctx->counts.p + 48, 0, 8, st));      // affine additions of this commit
   for (int s = 0; s < plan->n_sets; s++) {
     k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
         d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), (uint32_t*)ctx->keys.p,
@@ -186,6 +203,73 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
   const uint32_t* skeys = (const uint32_t*)(in_b ? ctx->skeys.p : ctx->keys.p);
   const uint32_t* srefs = (const uint32_t*)(in_b ? ctx->srefs.p : ctx->refs.p);
   if (pt) pt->mark(2);
+  // ---- batched-affine levels: add the entries of every bucket two by two while the list is long (affine_levels.cuh)
+  const uint32_t* acc_keys = skeys;
+  const uint32_t* acc_refs = srefs;
+  const void* acc_points = tab->d;
+  const uint32_t* acc_n = d_npairs;
+  size_t acc_bound = E;            // upper bound of *acc_n known to the host (grids are sized from it)
+  bool acc_direct = false;
+  {
+    const size_t key_space = (size_t)plan->n_sets * ((size_t)plan->B + 1);
+    int levels = affine_levels_for(ctx);
+    size_t bound[PA_MAX_LEVELS + 1];
+    bound[0] = E;
+    for (int l = 0; l < levels; l++) {
+      // every run leaves ceil(len / 2) entries; runs <= keys + tiles (a run is cut at tile edges)
+      size_t tiles = (bound[l] + PA_TILE - 1) / PA_TILE;
+      size_t runs = std::min(bound[l], key_space + tiles);
+      bound[l + 1] = (bound[l] + runs + 1) / 2;
+    }
+    const size_t tiles0 = (bound[0] + PA_TILE - 1) / PA_TILE, threads0 = tiles0 * PA_THREADS;
+    if (levels > 0) {
+      const size_t need_a = pa_list_bytes(bound[1]), need_b = levels > 1 ? pa_list_bytes(bound[2]) : 0;
+      const size_t need_w = pa_align((tiles0 + 1) * 8) + pa_align(threads0 * sizeof(PaMeta)) + threads0 * 64 + threads0 * PA_MAX_ADDS * 32 + 256;
+      size_t grow = (need_a > ctx->pa_a.cap ? need_a : 0) + (need_b > ctx->pa_b.cap ? need_b : 0) + (need_w > ctx->pa_work.cap ? need_w : 0);
+      size_t free_b = ~(size_t)0, total_b = 0;
+      if (grow) cudaMemGetInfo(&free_b, &total_b);             // only when something has to be allocated
+      if (grow && grow + ((size_t)2 << 30) > free_b) levels = 0;      // not worth evicting anything: the XYZZ path needs no extra memory
+      else if ((rc = ctx->pa_a.ensure(need_a)) || (rc = ctx->pa_b.ensure(need_b)) || (rc = ctx->pa_work.ensure(need_w)))
+        return rc;
+    }
+    uint32_t* d_counts = (uint32_t*)ctx->counts.p;             // [0] pairs, [1 + l] list length after level l
+    unsigned long long* d_adds = (unsigned long long*)((char*)ctx->counts.p + 48);
+    for (int l = 0; l < levels; l++) {
+      const unsigned tiles = (unsigned)((bound[l] + PA_TILE - 1) / PA_TILE);
+      const size_t threads = (size_t)tiles * PA_THREADS;
+      // pa_work: tile counts | tile offsets | per-thread meta | per-thread products | their inverses | per-addition prefixes
+      char* w = (char*)ctx->pa_work.p;
+      uint32_t* tile_cnt = (uint32_t*)w;
+      uint32_t* tile_off = tile_cnt + tiles0 + 1;
+      PaMeta* meta = (PaMeta*)(w + pa_align((size_t)(tiles0 + 1) * 8));
+      void* runs = (char*)meta + pa_align(threads0 * sizeof(PaMeta));
+      void* invs = (char*)runs + threads0 * 32;
+      void* pref = (char*)invs + threads0 * 32;
+      DevBuf& out = (l & 1) ? ctx->pa_b : ctx->pa_a;
+      uint32_t* keys_out = (uint32_t*)out.p;
+      void* pts_out = (char*)out.p + pa_keys_bytes(bound[l + 1]);
+      const unsigned inv_blocks = (unsigned)((threads / PA_INV_GROUP + 127) / 128 + 1);
+      if (l == 0) {
+        k_pa_up<CF, true><<<tiles, PA_THREADS, 0, st>>>(acc_keys, acc_refs, nullptr, tab->d, acc_n, tile_cnt, meta, pref, runs, d_adds);
+        k_pa_scan<<<1, 1024, 0, st>>>(acc_n, tile_cnt, tile_off, d_counts + 1 + l);
+        k_pa_inv<CF><<<inv_blocks, 128, 0, st>>>(runs, acc_n, invs);
+        k_pa_down<CF, true><<<tiles, PA_THREADS, 0, st>>>(acc_keys, acc_refs, nullptr, tab->d, acc_n, tile_off, meta, pref, invs, keys_out, pts_out);
+      } else {
+        k_pa_up<CF, false><<<tiles, PA_THREADS, 0, st>>>(acc_keys, nullptr, acc_points, nullptr, acc_n, tile_cnt, meta, pref, runs, d_adds);
+        k_pa_scan<<<1, 1024, 0, st>>>(acc_n, tile_cnt, tile_off, d_counts + 1 + l);
+        k_pa_inv<CF><<<inv_blocks, 128, 0, st>>>(runs, acc_n, invs);
+        k_pa_down<CF, false><<<tiles, PA_THREADS, 0, st>>>(acc_keys, nullptr, acc_points, nullptr, acc_n, tile_off, meta, pref, invs, keys_out, pts_out);
+      }
+      plan->launches += 4;
+      acc_keys = keys_out;
+      acc_refs = nullptr;
+      acc_points = pts_out;
+      acc_n = d_counts + 1 + l;
+      acc_bound = bound[l + 1];
+      acc_direct = true;
+    }
+    plan->affine_levels = levels;
+  }
   // ---- accumulate
   {
     // Entries per thread: as long as possible (each chunk edge that falls inside a bucket's run costs one XYZZ full
@@ -195,22 +279,27 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
     // Sized from the upper bound n*W; grids cover that bound and surplus threads exit on the device-side pair count.
     static const unsigned waves_env = [] { const char* e = getenv("MIRA_ACC_WAVES"); return e ? (unsigned)atoi(e) : 0u; }();
     static const int lmin = [] { const char* e = getenv("MIRA_ACC_LMIN"); return e ? atoi(e) : 32; }();
-    const unsigned waves = waves_env ? waves_env : (E < ((size_t)32 << 20) ? 2u : 4u);
-    int L = (int)(E / (148u * 512u * waves));
+    const size_t EA = acc_bound;
+    const unsigned waves = waves_env ? waves_env : (EA < ((size_t)32 << 20) ? 2u : 4u);
+    int L = (int)(EA / (148u * 512u * waves));
     L = L < lmin ? lmin : (L > 256 ? 256 : L);
-    uint32_t n_chunks = (uint32_t)((E + L - 1) / L);
+    uint32_t n_chunks = (uint32_t)((EA + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
-    k_accumulate<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(skeys, srefs, d_npairs, L, tab->d, ctx->buckets.p,
-                                                            (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
+    if (acc_direct)
+      k_accumulate<CF, true><<<(n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, nullptr, acc_n, L, acc_points, ctx->buckets.p,
+                                                                    (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
+    else
+      k_accumulate<CF, false><<<(n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, acc_refs, acc_n, L, acc_points, ctx->buckets.p,
+                                                                     (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
     uint32_t heavy_cap = n_chunks / HEAVY_CHUNKS + 2;
     if ((rc = ctx->cursor.ensure(((size_t)heavy_cap * 2 + 4) * 4))) return rc;
     uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0], [1] = counts, then the medium and the huge leader lists
     CU(cudaMemsetAsync(d_heavy, 0, 8, st));
-    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
+    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, acc_n, L,
                                                              ctx->buckets.p, d_heavy, heavy_cap);
-    k_combine_heavy<CF, 32><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs, L,
+    k_combine_heavy<CF, 32><<<148 * 2, HV_THREADS, 0, st>>>(acc_keys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, acc_n, L,
                                                            ctx->buckets.p, d_heavy, heavy_cap);
-    k_combine_heavy<CF, HV_THREADS><<<148 * 2, HV_THREADS, 0, st>>>(skeys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, d_npairs,
+    k_combine_heavy<CF, HV_THREADS><<<148 * 2, HV_THREADS, 0, st>>>(acc_keys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, acc_n,
                                                                    L, ctx->buckets.p, d_heavy, heavy_cap);
     plan->launches += 4;
   }

@@ -385,16 +385,17 @@ __global__ void __launch_bounds__(256) k_lookup_m(const void* __restrict__ l, co
 
 // out[i] = mul[i] * (in[i] + r)^{-1}  (mul == nullptr: 1), 0 when in[i] + r == 0  (evaluate_h_g, lookup.rs:307-319).
 // Thread t owns elements t, t + T, t + 2T, ... (coalesced), K at a time: Montgomery's trick — prefix products, ONE
-// inversion, back-substitution — so an element costs ~3 products plus 1/K of an inversion.
-constexpr int INV_K = 16;
-template <class F>
+// inversion, back-substitution — so an element costs ~3 products plus 1/K of an inversion.  All lanes invert at the
+// same time, hence the branch-uniform inversion (field.cuh); it is still worth ~190 products, so long vectors use
+// K = 64 (prefixes in local memory) and only short ones, which need the threads, K = 16.
+template <class F, int INV_K>
 __global__ void __launch_bounds__(128) k_shift_inv_mul(const void* __restrict__ in, const void* __restrict__ mul, size_t n, Fe<F> r,
                                                        void* __restrict__ out) {
   const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t base = t; base < n; base += T * INV_K) {
     Fe<F> pre[INV_K];                                   // pre[k] = product of the non-zero denominators before k
     Fe<F> acc = fe_one<F>();
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < INV_K; k++) {
       size_t i = base + (size_t)k * T;
       pre[k] = acc;
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(128) k_shift_inv_mul(const void* __restrict__ 
         if (!fe_is_zero(d)) acc = fe_mul(acc, d);
       }
     }
-    Fe<F> inv = fe_inv(acc);
-#pragma unroll
+    Fe<F> inv = fe_inv_uniform(acc);
+#pragma unroll 1
     for (int k = INV_K - 1; k >= 0; k--) {
       size_t i = base + (size_t)k * T;
       if (i < n) {
@@ -1086,8 +1087,11 @@ static int lookup_m_impl(const void* l, size_t n_l, const void* t, size_t n_t, v
 
 template <class F>
 static int shift_inv_impl(const void* in, const void* mul, size_t n, const void* r, void* out, cudaStream_t st) {
-  size_t threads = (n + mira::INV_K - 1) / mira::INV_K;
-  mira::k_shift_inv_mul<F><<<grid_for(threads, 128, 8), 128, 0, st>>>(in, mul, n, fe_from_host<F>(r), out);
+  if (n >= ((size_t)1 << 21)) {
+    mira::k_shift_inv_mul<F, 64><<<grid_for((n + 63) / 64, 128, 8), 128, 0, st>>>(in, mul, n, fe_from_host<F>(r), out);
+  } else {
+    mira::k_shift_inv_mul<F, 16><<<grid_for((n + 15) / 16, 128, 8), 128, 0, st>>>(in, mul, n, fe_from_host<F>(r), out);
+  }
   CU(cudaGetLastError());
   return MIRA_OK;
 }

@@ -131,8 +131,9 @@ def test_commit_edge_cases(gpu, curve):
         vals[i] = 1 << 200                                             # only one high window set
     sc = b"".join(R.to_mont_bytes(v, sm) for v in vals)
     ck = CommitmentKey(curve, bases)
-    for c in (0, 4, 11):
+    for c, levels in ((0, 0), (4, 0), (11, 0), (4, 3), (11, 6), (2, 2)):
         ck.set_window(c)
+        ck.set_affine_levels(levels)      # the batched-affine levels meet the same duplicates / negations / identities
         assert ck.commit(sc) == O.commit(curve, bases, sc)
         assert ck.commit(bytes(32 * n)) == IDENTITY                    # zero vector -> (0,0)
         assert ck.commit(sc[: 32 * 10]) == O.commit(curve, bases, sc[: 32 * 10])   # prefix of the key
@@ -386,6 +387,7 @@ def test_randomized_commit_configurations(gpu):
         ck.set_window(rng.choice([0, 0, 0, 2, 3, 7, 11, 16, 21]))
         ck.set_slice_min(rng.choice([0, 1, 50, 1 << 19]))
         ck.set_adaptive_window(rng.random() < 0.5)
+        ck.set_affine_levels(rng.choice([0, 0, 1, 2, 4, 6]))
         want = O.commit(curve, bases, sc)
         src = rng.choice(["bytes", "pinned", "device"])
         if src == "bytes":
@@ -396,3 +398,39 @@ def test_randomized_commit_configurations(gpu):
             d = torch.frombuffer(bytearray(sc) if sc else bytearray(32), dtype=torch.uint8).cuda()
             got = ck.commit_device(d.data_ptr(), n)
         assert got == want, (it, curve, n_key, n, dist, src, ck.stats())
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_batched_affine_levels_only_change_speed(gpu, curve):
+    """The experimental affine pre-reduction (mira_msm_set_affine_levels): every level count gives the oracle's bytes on
+    multi-tile lists (131 k points, ~1.7 M pairs), uniform and witness-like scalars (one bucket holding a third of all
+    pairs), a block of identical scalars on identical points (tangent additions at every level), through the sliced
+    host path and the batched commit."""
+    from mira_b200 import CommitmentKey
+    n = (1 << 17) + 11
+    bases_dev = gpu.gen_bases_dev(curve, 8181, n)
+    b = bytearray(gpu.to_bytes(bases_dev))
+    for i in range(5000, 5400):
+        b[64 * i:64 * i + 64] = b[64 * 4999:64 * 5000]            # 401 copies of one point
+    b[64 * 9:64 * 10] = bytes(64)                                  # an identity generator
+    b[64 * 11:64 * 12] = O.point_neg(curve, bytes(b[64 * 10:64 * 11]))
+    bases = bytes(b)
+    ck = CommitmentKey(curve, bases)
+    one = O.gen_scalars(curve, 8182, 1)
+    vectors = []
+    for dist in (0, 1):
+        sc = bytearray(O.gen_scalars(curve, 8183 + dist, n, dist))
+        sc[32 * 4999:32 * 5400] = one * 401                        # same scalar on the copies: P + P in every window
+        sc[32 * 11:32 * 12] = sc[32 * 10:32 * 11]                  # s*P + s*(-P): cancellation inside a bucket
+        vectors.append(bytes(sc))
+    want = [O.commit(curve, bases, v) for v in vectors]
+    for levels in (0, 1, 3, 6):
+        ck.set_affine_levels(levels)
+        for c in (0, 9):
+            ck.set_window(c)
+            ck.set_slice_min(0)
+            assert [ck.commit(v) for v in vectors] == want, (levels, c)
+            ck.set_slice_min(20_000)                               # four slices folded into live buckets
+            assert ck.commit(vectors[0]) == want[0], (levels, c, "sliced")
+        d = [torch.frombuffer(bytearray(v), dtype=torch.uint8).cuda() for v in vectors]
+        assert ck.commit_batch_device([t.data_ptr() for t in d], n) == want, (levels, "batch")

@@ -83,3 +83,13 @@ for k in (10, 16, 20, 24):
     nbytes = (1 << k) * 64 * (1 + max(k - 10, 0)) + (1 << k) * 64   # tile pass + one pass per global stage + bitrev
     print(json.dumps({"kernel": "fft", "log_n": k, "ms": round(ms, 3), "alg_GB_s": round(nbytes / ms / 1e6, 1),
                       "Melem_s": round((1 << k) / ms / 1e3, 1)}))
+
+# lookup argument (a6): multiplicities and the two inverse vectors, 2^22 elements (uniform values: all distinct)
+k = 22
+l_col, t_col = column(70, 1 << k, 0), column(71, 1 << k, 0)
+ms = timed(lambda: W.evaluate_m(FR, l_col, t_col), reps=3, warm=1)
+print(json.dumps({"kernel": "evaluate_m", "log_n": k, "ms": round(ms, 3), "Melem_s": round((1 << k) / ms / 1e3, 1)}))
+m_col = W.evaluate_m(FR, l_col, t_col)
+ms = timed(lambda: W.evaluate_h_g(FR, l_col, t_col, r, m_col), reps=3, warm=1)
+print(json.dumps({"kernel": "evaluate_h_g", "log_n": k, "ms": round(ms, 3), "Melem_s": round((1 << k) / ms / 1e3, 1),
+                  "alg_GB_s": round((1 << k) * 5 * 32 / ms / 1e6, 1)}))
