@@ -335,6 +335,8 @@ def run_fold_step(args):
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — mira_b200 has no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_fold_step_sharded(args, F)
     g = F.GpuFoldStep(args.log_rows)
 
     def timed(from_host, steps, warmup):
@@ -390,7 +392,8 @@ def run_fold_step(args):
                         "note": "integer-pipe bound kernel, see roofline_imad; the MSM kernels' roofline is in the default workload's line"},
            "roofline_imad": {"kernel": "k_eval_rows", "bound": "imad.wide.u32", "achieved": round(muls * MACS_PER_MODMUL / (ev_ms * 1e-3) / 1e12, 3),
                              "peak": round(imad_peak / 1e12, 3), "unit": "T wide-MAC/s",
-                             "frac": round(muls * MACS_PER_MODMUL / (ev_ms * 1e-3) / imad_peak, 4)}}
+                             "frac": round(muls * MACS_PER_MODMUL / (ev_ms * 1e-3) / imad_peak, 4)},
+           "commitments_sha256": __import__("hashlib").sha256(b"".join(res_dev)).hexdigest()}
     if not args.no_cpu_baseline:
         import oracle_lib as O
         cpu = F.CpuFoldStep(args.log_rows, inputs=g.host_inputs())
@@ -401,6 +404,74 @@ def run_fold_step(args):
         out["cpu_baseline"] = {"value": round(dt, 1), "unit": "ms", "cores": O.num_cores(), "kind": "port",
                                "sample": "one full step of the same workload (same bytes) through oracle/; commitments compared bit for bit"}
     print(json.dumps(out), flush=True)
+
+
+def run_fold_step_sharded(args, F):
+    """`--workload fold-step` under torchrun: the circuit's rows are cut into one range per rank (STRONG scaling: the
+    step is the same whatever N is).  Per step a rank queues its partial commitments, evaluation and folds on its own
+    stream; the one collective is an all_gather of 13 x 128 B per rank; every rank then folds the partials on its GPU."""
+    import torch
+    import torch.distributed as dist
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if "MIRA_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["MIRA_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+    dist.init_process_group("nccl", device_id=dev)
+    g = F.ShardedGpuFoldStep(args.log_rows, rank, world, device=local)
+    gathered = torch.empty(world * g.n_commits * 128, dtype=torch.uint8, device=dev)
+
+    def step():
+        part = g.step()
+        with torch.cuda.stream(g.stream):
+            dist.all_gather_into_tensor(gathered, part)
+        return g.combine(gathered, world)          # 13 commitments on every rank; returns when they are in host memory
+
+    for _ in range(args.warmup):
+        res = step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(g.stream)
+    for _ in range(args.steps):
+        res = step()
+    e1.record(g.stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    # every rank must hold the same commitments
+    digest = torch.tensor(list(b"".join(res)), dtype=torch.uint8, device=dev)
+    all_d = torch.empty(world * digest.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(all_d, digest)
+    same = bool((all_d.view(world, -1) == digest).all().item())
+    launches = sum(int(t["ck"].stats()["kernel_launches"]) for t in g.state)
+    if rank == 0:
+        assert same, "ranks disagree on the combined commitments"
+        ncommit = g.n_commits
+        out = {"metric": "IVC fold-step hot-path ms", "value": round(ms.item(), 3), "unit": "ms", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": round(ms.item(), 3), "higher_is_better": False, "scaling": "strong",
+               "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery, integer)", "data": "synthetic",
+               "config": {"workload": f"SnarkStar fold-step replay, k={args.log_rows}: witness commits + cross-term evaluation + "
+                                      f"cross-term commits + fold, both circuits", "points_per_step": F.points_per_step(g.sh),
+                          "commits_per_step": ncommit,
+                          "parallelism": f"row-range shards x{world}: local evaluation and folds, one all_gather of {ncommit} x 128 B XYZZ "
+                                         f"partials per rank, combine on every rank",
+                          "l2": "working set (keys' fixed-base tables, W, fixed columns) is >> 126 MB L2; no flush needed",
+                          "seed": F.SEED},
+               "clocks": clocks,
+               "e2e": None,
+               "gpu_launches": (2 * launches + 2 * len(g.state) * 2 + 2) * args.steps * world,
+               "commitments_sha256": __import__("hashlib").sha256(b"".join(res)).hexdigest()}
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

@@ -94,6 +94,18 @@ int mira_msm_partial(mira_msm_ctx *ctx, const void *scalars, size_t n, int scala
                      void *stream);
 /* out_affine (HOST, 64 B) = to_affine( sum of `count` XYZZ partials (HOST, 128 B each) ), on `device`. */
 int mira_msm_combine(int curve, const void *partials_xyzz, size_t count, int device, void *out_affine);
+/* The same for a row-sharded prover that keeps everything on the device: the XYZZ partial sums of `count` (<= 32)
+ * device vectors of length n against this rank's key shard, written to DEVICE memory (count x 128 B) on `stream`
+ * with no host synchronisation (one vector: sampled window as in mira_msm_commit_device; several: one batched
+ * pass as in mira_msm_commit_batch).  A rank queues all the commitments of a fold step into one buffer, gathers the
+ * ranks' buffers with a single all_gather and calls mira_msm_combine_dev. */
+int mira_msm_partial_batch_dev(mira_msm_ctx *ctx, const void *const *scalars_dev, size_t count, size_t n,
+                               void *out_xyzz_dev, void *stream);
+/* out_affine (HOST, n_commits x 64 B): out[j] = to_affine( sum over g < n_ranks of the XYZZ partial at
+ * partials_dev + g * rank_stride + j * 128 ) -- the layout an all_gather of the per-rank buffers produces.
+ * Runs on `device`/`stream` and returns when the results are in host memory. */
+int mira_msm_combine_dev(int curve, const void *partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride,
+                         int device, void *out_affine, void *stream);
 
 /* Page-lock a host buffer the caller will commit from repeatedly (a witness column arena, the `Vec<C::Scalar>` a
  * prover re-uses every step).  mira_msm_commit works with any host memory, but only page-locked memory lets the

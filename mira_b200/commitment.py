@@ -200,6 +200,13 @@ class CommitmentKey:
         _check(N.lib().mira_msm_partial(self._ctx, ptr, n, 1 if on_device else 0, out, stream or None), n, self._n)
         return out.raw
 
+    def partial_batch_device(self, scalar_dev_ptrs, n: int, out_dev_ptr: int, stream: int = 0):
+        """XYZZ partial sums (128 B each) of `scalar_dev_ptrs` against this key shard, written to device memory at
+        `out_dev_ptr` on `stream` without synchronising the host (row-sharded provers)."""
+        k = len(scalar_dev_ptrs)
+        ptrs = (C.c_void_p * max(k, 1))(*scalar_dev_ptrs)
+        _check(N.lib().mira_msm_partial_batch_dev(self._ctx, ptrs, k, n, out_dev_ptr, stream or None), n, self._n)
+
     def stats(self) -> dict:
         st = N.MsmStats()
         _check(N.lib().mira_msm_get_stats(self._ctx, C.byref(st)))
@@ -233,6 +240,15 @@ class CommitmentKey:
             self.close()
         except Exception:
             pass
+
+
+def combine_partials_device(curve: int, partials_dev_ptr: int, n_ranks: int, n_commits: int, rank_stride: int, device: int = 0,
+                            stream: int = 0):
+    """Commitments from the gathered per-rank partial buffers (device memory, `[rank][commit]` x 128 B with
+    `rank_stride` bytes between ranks): sums over the ranks, normalises, returns `n_commits` 64-byte points."""
+    out = C.create_string_buffer(POINT_BYTES * max(n_commits, 1))
+    _check(N.lib().mira_msm_combine_dev(curve, partials_dev_ptr, n_ranks, n_commits, rank_stride, device, out, stream or None))
+    return [out.raw[POINT_BYTES * i:POINT_BYTES * (i + 1)] for i in range(n_commits)]
 
 
 def combine_partials(curve: int, partials: bytes, device: int = 0) -> bytes:

@@ -93,6 +93,8 @@ struct CurveOps {
   int (*prepare)(mira_msm_ctx*, size_t n);
   int (*check_on_curve)(mira_msm_ctx*);
   int (*combine)(const void* partials_host, size_t count, void* out_affine_host);
+  int (*partial_batch_dev)(mira_msm_ctx*, const void* const* scalar_sets_dev, size_t count, size_t n, void* out_xyzz_dev, cudaStream_t st);
+  int (*combine_dev)(const void* partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride, void* out_affine_host, cudaStream_t st);
   int (*gen_scalars)(uint64_t seed, size_t first, size_t n, int dist, void* out_dev);
   int (*gen_bases)(uint64_t seed, size_t first, size_t n, void* out_dev);
   int (*test_point_op)(int op, const void* p_dev, const void* q_dev, size_t n, void* out_dev);

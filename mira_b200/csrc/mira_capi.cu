@@ -185,6 +185,30 @@ int mira_msm_combine(int curve, const void* partials, size_t count, int device, 
   return ops_for(curve).combine(partials, count, out_affine);
 }
 
+int mira_msm_partial_batch_dev(mira_msm_ctx* ctx, const void* const* scalars_dev, size_t count, size_t n, void* out_xyzz_dev, void* stream) {
+  if (!ctx || (count && (!scalars_dev || !out_xyzz_dev))) return fail(MIRA_ERR_INVALID, "null argument");
+  if (count > 32) return fail(MIRA_ERR_INVALID, "at most 32 vectors per batched commit");
+  if (n > ctx->n_bases)
+    return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
+  for (size_t k = 0; k < count; k++)
+    if (n && !scalars_dev[k]) return fail(MIRA_ERR_INVALID, "vector %zu is null", k);
+  if (!count) return MIRA_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return ops_for(ctx->curve).partial_batch_dev(ctx, scalars_dev, count, n, out_xyzz_dev, st);
+}
+
+int mira_msm_combine_dev(int curve, const void* partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride, int device,
+                         void* out_affine, void* stream) {
+  if (n_commits && (!out_affine || (n_ranks && !partials_dev))) return fail(MIRA_ERR_INVALID, "null argument");
+  if (!valid_curve(curve)) return fail(MIRA_ERR_INVALID, "unknown curve %d", curve);
+  if (rank_stride < n_commits * 128 || rank_stride % 32) return fail(MIRA_ERR_INVALID, "rank stride %zu does not hold %zu partials", rank_stride, n_commits);
+  if (!n_commits) return MIRA_OK;
+  CU(cudaSetDevice(device));
+  return ops_for(curve).combine_dev(partials_dev, n_ranks, n_commits, rank_stride, out_affine, (cudaStream_t)stream);
+}
+
 int mira_msm_get_stats(const mira_msm_ctx* ctx, mira_msm_stats* out) {
   if (!ctx || !out) return fail(MIRA_ERR_INVALID, "null argument");
   *out = ctx->stats;

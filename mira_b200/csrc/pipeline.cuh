@@ -512,6 +512,57 @@ int commit_batch_impl(mira_msm_ctx* ctx, const void* const* d_scalar_sets, size_
   return MIRA_OK;
 }
 
+// Row-sharded provers: `count` vectors against this rank's key shard, the un-normalised XYZZ sums
+// (count x 128 B) written to DEVICE memory on `st` without a host round trip, so that a rank can queue all the
+// commitments of a fold step, all_gather them once and combine.  One vector goes through the adaptive-window path
+// (witness columns are sparse), several through the batched one.
+template <class CF, class SF>
+int partial_batch_dev_impl(mira_msm_ctx* ctx, const void* const* d_scalar_sets, size_t count, size_t n, void* d_out, cudaStream_t st) {
+  int rc;
+  if ((rc = ctx->result.ensure(count * 192 + 256))) return rc;
+  if (n == 0) {
+    CU(cudaMemsetAsync(d_out, 0, count * 128, st));
+    ctx->stats = mira_msm_stats{};
+    return MIRA_OK;
+  }
+  if (count == 1) {
+    if ((rc = msm_device<CF, SF>(ctx, d_scalar_sets[0], n, st))) return rc;
+  } else {
+    MsmPlan plan;
+    if ((rc = msm_begin<CF>(ctx, n, n, st, &plan, (int)count))) return rc;
+    if ((rc = msm_slice<CF, SF>(ctx, &plan, d_scalar_sets, 0, n, false, st, nullptr))) return rc;
+    if ((rc = msm_finish<CF>(ctx, &plan, st, nullptr))) return rc;
+  }
+  CU(cudaMemcpyAsync(d_out, ctx->result.p, count * 128, cudaMemcpyDeviceToDevice, st));
+  return MIRA_OK;
+}
+
+// out[j] = to_affine( sum over ranks g of partials[g * rank_stride + j * 128] ), j < n_commits; partials on the device
+// (as an all_gather leaves them), results to the host.
+template <class CF>
+__global__ void k_combine_partials(const void* __restrict__ partials, uint32_t n_ranks, size_t rank_stride, void* __restrict__ out_affine) {
+  if (threadIdx.x) return;
+  Xyzz<CF> acc = xyzz_identity<CF>();
+  for (uint32_t g = 0; g < n_ranks; g++) {
+    Xyzz<CF> p = xyzz_load<CF>(reinterpret_cast<const char*>(partials) + (size_t)g * rank_stride + (size_t)blockIdx.x * 128);
+    xyzz_add(acc, p);
+  }
+  aff_store<CF>(reinterpret_cast<char*>(out_affine) + (size_t)blockIdx.x * 64, xyzz_to_affine(acc));
+}
+
+template <class CF>
+int combine_dev_impl(const void* d_partials, size_t n_ranks, size_t n_commits, size_t rank_stride, void* out_affine_host, cudaStream_t st) {
+  void* d = nullptr;
+  CU(cudaMallocAsync(&d, n_commits * 64, st));
+  k_combine_partials<CF><<<(unsigned)n_commits, 32, 0, st>>>(d_partials, (uint32_t)n_ranks, rank_stride, d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_affine_host, d, n_commits * 64, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(d, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "combine failed: %s", cudaGetErrorString(e));
+  return MIRA_OK;
+}
+
 template <class CF>
 int prepare_impl(mira_msm_ctx* ctx, size_t n) {
   int c = ctx->forced_window ? ctx->forced_window : choose_window(n);

@@ -135,6 +135,94 @@ class GpuFoldStep:
         return out
 
 
+# ------------------------------------------------------------------------------------------ GPU arm, row-sharded
+class ShardedGpuFoldStep:
+    """The same fold step with the 2^k rows cut into `world` contiguous ranges, one per rank (cross-term
+    evaluation and the fold shard by row range with no exchange; the commitments shard by point range).
+
+    Rank g holds rows [lo, hi) of every column.  Its key shard is laid out column by column,
+    `ck[c * 2^k + lo .. c * 2^k + hi)` for c = 0 .. num_advice - 1, so that the local witness (the same rows of each
+    advice column, concatenated) commits against the whole shard and a local cross-term vector against its first
+    `hi - lo` points — exactly the key prefix the unsharded `ck.commit(T_j)` uses.  MainGate queries `Rotation::cur()`
+    only (asserted), so a row needs no neighbour and the evaluator runs on the local columns as a smaller circuit.
+    Every commitment becomes a 128-byte XYZZ partial in one device buffer; `gather` is the single collective
+    (all_gather of 13 x 128 B per rank) and `combine` folds the ranks' partials on the device."""
+
+    def __init__(self, log_rows: int, rank: int, world: int, device: int = 0):
+        import torch
+        import gpu_util
+        from mira_b200 import CommitmentKey
+        from mira_b200 import witness as W
+        from mira_b200.sharding import shard_range
+        self.torch, self.W = torch, W
+        self.rank, self.world, self.device = rank, world, device
+        self.sh = shapes(log_rows)
+        self.stream = torch.cuda.Stream(device=device)
+        self.state = []
+        self.n_commits = sum(1 + len(s["progs"]) for s in self.sh)
+        self.partials = torch.zeros(self.n_commits * 128, dtype=torch.uint8, device=f"cuda:{device}")
+        for ci, s in enumerate(self.sh):
+            rows, curve, cols = s["rows"], s["curve"], s["meta"]["num_advice"]
+            lo, hi = shard_range(rows, world, rank)
+            loc = hi - lo
+            assert all(r == 0 for p in s["progs"] for r in p["rotations"]), "row sharding without a halo needs Rotation::cur() only"
+            gen = lambda seed, n, dist, first=0: gpu_util.gen_scalars_dev(curve, SEED + 1000 * ci + seed, n, dist, first=first, device=device)
+            col_major = lambda seed, dist: torch.cat([gen(seed, loc, dist, first=c * rows + lo) for c in range(cols)])
+            bases = torch.cat([gpu_util.gen_bases_dev(curve, SEED + ci, loc, first=c * rows + lo, device=device) for c in range(cols)])
+            ck = CommitmentKey(curve, bases, device=device, on_device=True)
+            ck.prepare(cols * loc)
+            ck.prepare(loc)
+            del bases
+            st = {"ck": ck, "loc": loc, "n_w": cols * loc,
+                  "fixed": [gen(10 + i, loc, 1, first=lo) for i in range(s["meta"]["num_fixed"])],
+                  "W1": col_major(1, 0), "E": gen(2, loc, 0, first=lo), "W2": col_major(3, 1),
+                  "W_out": torch.empty(cols * loc * 32, dtype=torch.uint8, device=f"cuda:{device}"),
+                  "E_out": torch.empty(loc * 32, dtype=torch.uint8, device=f"cuda:{device}"),
+                  "T": [torch.empty(loc * 32, dtype=torch.uint8, device=f"cuda:{device}") for _ in s["progs"]],
+                  "ch": gpu_util.to_bytes(gen(4, s["meta"]["num_challenges"], 0)),
+                  "r": gpu_util.to_bytes(gen(5, 1, 0)),
+                  "progs": [W.GraphEvaluator(s["field"], p["code"], p["constants"], p["rotations"], p["num_intermediates"])
+                            for p in s["progs"]]}
+            self.state.append(st)
+        torch.cuda.synchronize()
+
+    def step(self):
+        """Queues the rank's share of the step; returns the device buffer of its n_commits XYZZ partials."""
+        torch, W = self.torch, self.W
+        sh = self.stream.cuda_stream
+        base = self.partials.data_ptr()
+        j = 0
+        with torch.cuda.stream(self.stream):
+            for s, st in zip(self.sh, self.state):
+                ck = st["ck"]
+                ck.partial_batch_device([st["W2"].data_ptr()], st["n_w"], base + 128 * j, sh)
+                j += 1
+                dom = W.PlonkEvalDomain(s["meta"]["num_advice"], 0, st["ch"], [], st["fixed"], [st["W1"]], [st["W2"]])
+                W.evaluate_rows_multi(st["progs"], dom, outs=st["T"], stream=sh)
+                ck.partial_batch_device([t.data_ptr() for t in st["T"]], st["loc"], base + 128 * j, sh)
+                j += len(st["T"])
+                W.fold_w(s["field"], st["W1"], st["W2"], st["r"], out=st["W_out"], stream=sh)
+                W.fold_e(s["field"], st["E"], st["T"], st["r"], out=st["E_out"], stream=sh)
+        return self.partials
+
+    def curves(self):
+        """Curve of each commitment slot, in the order `step` writes them."""
+        return [s["curve"] for s in self.sh for _ in range(1 + len(s["progs"]))]
+
+    def combine(self, gathered, world: int):
+        """`gathered`: device tensor [world][n_commits][128] (what all_gather of the ranks' buffers gives).  Returns the
+        commitments in the unsharded step's order.  Both circuits' slots are combined by their own curve."""
+        from mira_b200 import combine_partials_device
+        out, j = [], 0
+        with self.torch.cuda.stream(self.stream):
+            for s in self.sh:
+                cnt = 1 + len(s["progs"])
+                out += combine_partials_device(s["curve"], gathered.data_ptr() + 128 * j, world, cnt, self.n_commits * 128,
+                                               self.device, self.stream.cuda_stream)
+                j += cnt
+        return out
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 class CpuFoldStep:
     """The same step through oracle/ (test infrastructure: only bench.py's CPU legs and tests use this)."""
