@@ -95,6 +95,21 @@ class CommitmentKey {
     return out;
   }
 
+  // `cross_terms.iter().map(|v| ck.commit(v))` (src/nifs/vanilla/mod.rs:124-127) in one call: device vectors of length n
+  std::vector<Affine> commit_batch(const std::vector<const void*>& scalars_dev, size_t n, void* stream = nullptr) const {
+    if (n > n_) throw TooLongInput(n, n_);
+    std::vector<Affine> out(scalars_dev.size());
+    check(mira_msm_commit_batch(ctx_, scalars_dev.data(), scalars_dev.size(), n, out.data(), stream), n);
+    return out;
+  }
+  // Row-/point-range-sharded provers (one process per GPU): this rank's XYZZ partial sums (128 B each) of the vectors,
+  // written to device memory on `stream` without a host round trip; all_gather the ranks' buffers, then
+  // combine_partials_device.
+  void partial_batch_device(const std::vector<const void*>& scalars_dev, size_t n, void* out_xyzz_dev, void* stream = nullptr) const {
+    if (n > n_) throw TooLongInput(n, n_);
+    check(mira_msm_partial_batch_dev(ctx_, scalars_dev.data(), scalars_dev.size(), n, out_xyzz_dev, stream), n);
+  }
+
   // src/commitment.rs:109-124: the file is the memory image of [C], 64 << k bytes.
   static CommitmentKey load_from_file(const char* path, unsigned k, int device = 0) {
     size_t n = size_t(1) << k;
@@ -124,5 +139,17 @@ class CommitmentKey {
   mira_msm_ctx* ctx_ = nullptr;
   size_t n_ = 0;
 };
+
+// out[j] = to_affine(sum over ranks of the partial at partials_dev + g * rank_stride + j * 128): the layout an all_gather
+// of the per-rank buffers of partial_batch_device leaves on the device.
+template <class Curve>
+inline std::vector<Affine> combine_partials_device(const void* partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride,
+                                                   int device = 0, void* stream = nullptr) {
+  std::vector<Affine> out(n_commits);
+  int rc = mira_msm_combine_dev(Curve::id, partials_dev, n_ranks, n_commits, rank_stride, device, out.data(), stream);
+  if (rc == MIRA_ERR_INVALID) throw std::invalid_argument(mira_last_error());
+  if (rc != MIRA_OK) throw CudaError(mira_last_error());
+  return out;
+}
 
 }  // namespace mira

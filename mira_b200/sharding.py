@@ -11,7 +11,7 @@ replacement for rayon's chunk-per-thread split inside halo2's best_multiexp.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Tuple
 
 PARTIAL_BYTES = 128
 
@@ -31,6 +31,19 @@ def shard_of_prefix(n_commit: int, key_lo: int, key_hi: int) -> Tuple[int, int]:
     lo = min(key_lo, n_commit)
     hi = min(key_hi, n_commit)
     return lo, hi
+
+
+def row_shard_key_ranges(rows: int, columns: int, world: int, rank: int) -> List[Tuple[int, int]]:
+    """Key index ranges of a ROW-sharded prover (evaluation and fold shard by row range).
+
+    The witness is `columns` advice columns of `rows` rows, concatenated column by column
+    (`concatenate_with_padding`, src/util.rs:189-193), so key point `c * rows + r` belongs to row r of column c.  A rank
+    that owns rows [lo, hi) therefore needs `ck[c * rows + lo .. c * rows + hi)` for every column c, in this order:
+    its local witness (the same rows of each column, concatenated) then commits against the whole local key, and a
+    local cross-term vector (one value per owned row) against the first range — the prefix the unsharded
+    `ck.commit(T)` uses."""
+    lo, hi = shard_range(rows, world, rank)
+    return [(c * rows + lo, c * rows + hi) for c in range(columns)]
 
 
 class ShardedCommitmentKey:

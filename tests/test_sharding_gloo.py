@@ -105,3 +105,87 @@ def test_sharded_commit_over_gloo(world, curve, n_key, n_commit):
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res["ok"] and res["toolong"]
+
+
+# ---------------------------------------------------------------------------------- row-sharded fold step
+def test_row_shard_key_ranges_cover_the_key_once():
+    from mira_b200.sharding import row_shard_key_ranges
+    for rows, cols, world in ((64, 7, 2), (64, 14, 3), (1 << 19, 14, 8), (5, 3, 4)):
+        seen = []
+        for r in range(world):
+            rg = row_shard_key_ranges(rows, cols, world, r)
+            assert len(rg) == cols
+            assert len({hi - lo for lo, hi in rg}) == 1                      # the same rows of every column
+            assert rg[0] == shard_range(rows, world, r)                      # first range = the cross terms' key prefix
+            seen += [i for lo, hi in rg for i in range(lo, hi)] if rows <= 64 else []
+        if rows <= 64:
+            assert sorted(seen) == list(range(rows * cols))
+
+
+def _fold_worker(rank, world, port, q):
+    """One fold step of the secondary circuit (k = 6) with the rows cut across `world` ranks: local evaluation, local
+    commitments and local fold through the CPU oracle, ONE all_gather of the partial commitments, sum on rank 0."""
+    import torch.distributed as dist
+    import graph_evaluator_model as G
+    import oracle_lib as O
+    import pyref as R
+    from mira_b200.sharding import row_shard_key_ranges
+    from witness_util import pack_program
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        curve, field, rows = R.GRUMPKIN, R.FQ, 64
+        progs, meta = G.cross_term_programs(5, 1, R.P)
+        progs = [pack_program(p) for p in progs]
+        cols = meta["num_advice"]
+        assert all(r == 0 for p in progs for r in p["rotations"])
+        n_w = cols * rows
+        bases = O.gen_bases(curve, 11, n_w)
+        fixed = [O.gen_scalars(curve, 20 + i, rows, 1) for i in range(meta["num_fixed"])]
+        w1, w2, e = O.gen_scalars(curve, 1, n_w, 0), O.gen_scalars(curve, 3, n_w, 1), O.gen_scalars(curve, 2, rows, 0)
+        ch, r_ = O.gen_scalars(curve, 4, meta["num_challenges"], 0), O.gen_scalars(curve, 5, 1, 0)
+
+        def step(key, fx, a1, a2, ee, n_rows):
+            dom = {"row_size": n_rows, "fixed": fx, "w1": [a1], "w2": [a2], "challenges": ch, "num_advice": cols}
+            ts = [O.eval_rows(field, p, dom) for p in progs]
+            commits = [O.commit(curve, key, a2)] + [O.commit(curve, key[:64 * n_rows], t) for t in ts]
+            return commits, O.fold_w(field, a1, a2, r_), O.fold_e(field, ee, ts, r_)
+
+        ranges = row_shard_key_ranges(rows, cols, world, rank)
+        lo, hi = ranges[0]
+        cut = lambda v, size: b"".join(v[size * a:size * b] for a, b in ranges)            # the rank's rows of every column
+        part, w_loc, e_loc = step(cut(bases, 64), [f[32 * lo:32 * hi] for f in fixed], cut(w1, 32), cut(w2, 32), e[32 * lo:32 * hi], hi - lo)
+        mine = torch.frombuffer(bytearray(b"".join(part)), dtype=torch.uint8)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)                                                  # the only exchange
+        if rank == 0:
+            want, w_all, e_all = step(bases, fixed, w1, w2, e, rows)
+            got = []
+            for j in range(len(part)):
+                acc = bytes(64)
+                for g in gathered:
+                    acc = O.point_add(curve, acc, g.numpy().tobytes()[64 * j:64 * j + 64])
+                got.append(acc)
+            q.put(("commits", got == want))
+        else:
+            w_all = O.fold_w(field, w1, w2, r_)
+            e_all = None
+        q.put((f"fold{rank}", w_loc == cut(w_all, 32) and (e_all is None or e_loc == e_all[32 * lo:32 * hi])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_fold_step_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fold_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world + 1))
+    assert res["commits"] and all(res[f"fold{r}"] for r in range(world))

@@ -153,7 +153,7 @@ class ShardedGpuFoldStep:
         import gpu_util
         from mira_b200 import CommitmentKey
         from mira_b200 import witness as W
-        from mira_b200.sharding import shard_range
+        from mira_b200.sharding import row_shard_key_ranges, shard_range
         self.torch, self.W = torch, W
         self.rank, self.world, self.device = rank, world, device
         self.sh = shapes(log_rows)
@@ -168,7 +168,8 @@ class ShardedGpuFoldStep:
             assert all(r == 0 for p in s["progs"] for r in p["rotations"]), "row sharding without a halo needs Rotation::cur() only"
             gen = lambda seed, n, dist, first=0: gpu_util.gen_scalars_dev(curve, SEED + 1000 * ci + seed, n, dist, first=first, device=device)
             col_major = lambda seed, dist: torch.cat([gen(seed, loc, dist, first=c * rows + lo) for c in range(cols)])
-            bases = torch.cat([gpu_util.gen_bases_dev(curve, SEED + ci, loc, first=c * rows + lo, device=device) for c in range(cols)])
+            bases = torch.cat([gpu_util.gen_bases_dev(curve, SEED + ci, k_hi - k_lo, first=k_lo, device=device)
+                               for k_lo, k_hi in row_shard_key_ranges(rows, cols, world, rank)])
             ck = CommitmentKey(curve, bases, device=device, on_device=True)
             ck.prepare(cols * loc)
             ck.prepare(loc)
