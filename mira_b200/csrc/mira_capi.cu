@@ -121,7 +121,8 @@ void mira_msm_ctx_destroy(mira_msm_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& t : ctx->tables) cudaFree(t.d);
   for (DevBuf* b : {&ctx->scalars, &ctx->keys, &ctx->refs, &ctx->skeys, &ctx->srefs, &ctx->counts, &ctx->cursor, &ctx->tile_sums,
-                    &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->result})
+                    &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->result, &ctx->pa_a, &ctx->pa_b,
+                    &ctx->pa_work})
     b->release();
   if (ctx->d_bases) cudaFree(ctx->d_bases);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
