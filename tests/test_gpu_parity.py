@@ -434,3 +434,32 @@ def test_batched_affine_levels_only_change_speed(gpu, curve):
             assert ck.commit(vectors[0]) == want[0], (levels, c, "sliced")
         d = [torch.frombuffer(bytearray(v), dtype=torch.uint8).cuda() for v in vectors]
         assert ck.commit_batch_device([t.data_ptr() for t in d], n) == want, (levels, "batch")
+
+
+def test_contexts_release_their_device_memory(gpu):
+    """Create / use / destroy in a loop: the free device memory must come back (every workspace, the fixed-base tables
+    and the optional affine-level buffers are owned by the context)."""
+    from mira_b200 import CommitmentKey
+    curve, n = R.BN254, 20_000
+    bases = O.gen_bases(curve, 91, n)
+    sc = O.gen_scalars(curve, 92, n)
+    want = O.commit(curve, bases, sc)
+
+    def once(levels):
+        ck = CommitmentKey(curve, bases)
+        ck.set_affine_levels(levels)
+        assert ck.commit(sc) == want
+        d = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
+        assert ck.commit_batch_device([d.data_ptr(), d.data_ptr()], n) == [want, want]
+        ck.close()
+
+    once(2)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free0, _ = torch.cuda.mem_get_info()
+    for it in range(12):
+        once(it % 3)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 32 << 20, f"{(free0 - free1) >> 20} MiB not returned after 12 create/destroy cycles"
