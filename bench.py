@@ -36,7 +36,7 @@ IMAD_WIDE_PER_CLK_PER_SM = 32    # measured, profiles/r01_intpipe_microbench.jso
 MACS_PER_MODMUL = 136            # 8-limb CIOS: 2*8^2 + 8
 MODMUL_PER_MADD = 10             # XYZZ mixed add 8M + 2S (canonical count: 1,360 wide MACs per pair)
 MACS_PER_MADD_EXECUTED = 8 * 136 + 200   # 8 products + one dual product a*b + c*d under a single reduction (192 + 8)
-ACC_DRAM_BYTES_PER_PAIR = 29.12e9 / 201326592   # measured, profiles/r01_accumulate_v9.txt
+ACC_DRAM_BYTES_PER_PAIR = 29.08e9 / 201326592   # measured, profiles/r01_accumulate_v12.txt
 
 
 def measured_peaks():
@@ -235,7 +235,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_accumulate (+k_combine)", "bound": "hbm", "achieved": round(alg_bytes / acc_s / 1e9, 1),
                      "peak": hbm_peak, "unit": "GB/s", "frac": round(alg_bytes / acc_s / 1e9 / hbm_peak, 4),
                      "traffic": round(entries * ACC_DRAM_BYTES_PER_PAIR / 1e9, 2), "traffic_unit": "GB per launch",
-                     "traffic_source": "ncu --set full, profiles/r01_accumulate_v9.txt: 29.12 GB dram read+write for 201.3 M pairs "
+                     "traffic_source": "ncu --set full, profiles/r01_accumulate_v12.txt: 29.08 GB dram read+write for 201.3 M pairs "
                                        "(each 64 B gathered point costs a 128 B DRAM burst), scaled to this launch's pairs",
                      "peak_source": peak_src,
                      "note": "kernel is integer-pipe bound, see roofline_imad"},
