@@ -463,3 +463,32 @@ def test_contexts_release_their_device_memory(gpu):
     torch.cuda.empty_cache()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 32 << 20, f"{(free0 - free1) >> 20} MiB not returned after 12 create/destroy cycles"
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_reference_digest_kat_on_the_gpu(gpu, curve):
+    """The reference's own curve-level known answer, `digest::tests::consistency` (src/digest.rs:99-114):
+    (r - 1) * G == -G for bn256, written with literal bytes — G = (1, 2), so -G = (1, p - 2) — and no oracle in the loop.
+    Run through every commit route that can differ (windows, device / host scalars, batch, affine levels).  The Grumpkin
+    line is the same identity on the cycle's other curve (generator (1, sqrt(-16)) taken from the oracle)."""
+    from mira_b200 import CommitmentKey
+    pm, sm = R.base_mod(curve), R.scalar_mod(curve)
+    if curve == R.BN254:
+        g = R.to_mont_bytes(1, pm) + R.to_mont_bytes(2, pm)
+        neg_g = R.to_mont_bytes(1, pm) + R.to_mont_bytes(pm - 2, pm)
+    else:
+        g = O.generator(curve)
+        neg_g = O.point_neg(curve, g)
+    s = R.to_mont_bytes(sm - 1, sm)
+    ck = CommitmentKey(curve, g)
+    for c in (0, 2, 7, 16, 22):
+        ck.set_window(c)
+        for levels in (0, 2):
+            ck.set_affine_levels(levels)
+            assert ck.commit(s) == neg_g
+            d = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
+            assert ck.commit_device(d.data_ptr(), 1) == neg_g
+            assert ck.commit_batch_device([d.data_ptr(), d.data_ptr()], 1) == [neg_g, neg_g]
+    # and on a longer key: s * G + 1 * G == identity
+    two = CommitmentKey(curve, g + g)
+    assert two.commit(s + R.to_mont_bytes(1, sm)) == bytes(64)
