@@ -492,3 +492,32 @@ def test_reference_digest_kat_on_the_gpu(gpu, curve):
     # and on a longer key: s * G + 1 * G == identity
     two = CommitmentKey(curve, g + g)
     assert two.commit(s + R.to_mont_bytes(1, sm)) == bytes(64)
+
+
+def test_reference_lagrange_kat_on_the_gpu(gpu):
+    """`lagrange::tests` known answers (src/polynomial/lagrange.rs:113-126, committed as tests/golden/lagrange_kat_fr.json):
+    L_i(2) on the 2^2 domain, computed with the DEVICE field kernels only (multiplication, subtraction, inversion,
+    Montgomery conversions) from integer literals — no oracle in the loop."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lagrange_kat_fr.json")) as f:
+        want = [int(v) for v in json.load(f)["raw_strings"]]
+    MUL, SUB, INV, TO_CANON, FROM_CANON = 0, 2, 4, 5, 6
+    fr = lambda v: gpu.field_op(R.FR, FROM_CANON, (v % R.R_).to_bytes(32, "little"), bytes(32))
+    op = lambda o, a, b=None: gpu.field_op(R.FR, o, a, b if b is not None else bytes(32))
+    root = 0x03ddb9f5166d18b798865ea93dd31f743215cf6dd39329c8d34f1ed960c37c9c     # halo2curves Fr::ROOT_OF_UNITY (SURVEY.md 8c)
+    w = fr(root)
+    for _ in range(2, 28):                        # get_omega_or_inv (src/fft.rs:12-24): omega of the 2^2 domain
+        w = op(MUL, w, w)
+    n, X = 4, fr(2)
+    xn = fr(1)
+    for _ in range(n):
+        xn = op(MUL, xn, X)
+    num, ninv = op(SUB, xn, fr(1)), op(INV, fr(n))
+    wi, got = fr(1), []
+    for _ in range(n):
+        den = op(INV, op(SUB, X, wi))
+        v = op(MUL, op(MUL, wi, ninv), op(MUL, num, den))
+        got.append(int.from_bytes(op(TO_CANON, v), "little"))
+        wi = op(MUL, wi, w)
+    assert got == want
