@@ -261,6 +261,18 @@ def test_concat_pad(W):
     assert host(W.concatenate_with_padding([dev(c) for c in big], 1024)) == O.concat_pad(big, 1024)
 
 
+@pytest.mark.parametrize("cols,pad,want", [  # the reference's own tests, src/util.rs:208-263
+    ([], 4, []),
+    ([[1, 2]], 4, [1, 2, 0, 0]),
+    ([[1, 2, 3, 4]], 4, [1, 2, 3, 4]),
+    ([[1, 2], [3], [4, 5, 6]], 4, [1, 2, 0, 0, 3, 0, 0, 0, 4, 5, 6, 0]),
+    ([[1], [2, 3]], 1, [1, 2, 3]),
+])
+def test_concat_pad_reference_cases(W, cols, pad, want):
+    got = host(W.concatenate_with_padding([dev(mont(c, M)) for c in cols], pad))
+    assert unmont(got, M) == want
+
+
 # ---- FFT (src/fft.rs)
 def test_fft_reference_kat(W):
     with open(os.path.join(GOLDEN, "fft_kat_fr.json")) as f:

@@ -163,6 +163,20 @@ def test_concat_pad():
     assert O.concat_pad([], 4) == b""
 
 
+REFERENCE_CONCAT_CASES = [  # the reference's own tests, src/util.rs:208-263
+    ([], 4, []),
+    ([[1, 2]], 4, [1, 2, 0, 0]),
+    ([[1, 2, 3, 4]], 4, [1, 2, 3, 4]),
+    ([[1, 2], [3], [4, 5, 6]], 4, [1, 2, 0, 0, 3, 0, 0, 0, 4, 5, 6, 0]),
+    ([[1], [2, 3]], 1, [1, 2, 3]),
+]
+
+
+@pytest.mark.parametrize("cols,pad,want", REFERENCE_CONCAT_CASES)
+def test_concat_pad_reference_cases(cols, pad, want):
+    assert unmont(O.concat_pad([mont(c, M) for c in cols], pad), M) == want
+
+
 # ---- FFT (src/fft.rs)
 def test_fft_kat_from_reference_golden():
     """tests/golden/fft_kat_fr.json holds the vector of src/fft.rs:239-258 verbatim."""
