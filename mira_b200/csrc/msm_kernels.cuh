@@ -374,7 +374,14 @@ __global__ void __launch_bounds__(128) k_sum_points(const void* __restrict__ in_
   char* my = reinterpret_cast<char*>(sm) + threadIdx.x * 128;
   xyzz_store<CF>(my, acc);
   __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+  // tree over the threads that hold data only (the last launches of a reduction see a handful of points: every level
+  // skipped is one ~7 us group addition off the critical path of a small commit)
+  const uint32_t first = blockIdx.x * per_block;
+  const uint32_t have = first < n ? (n - first < per_block ? n - first : per_block) : 0u;
+  const uint32_t holders = (have + per_thread - 1) / per_thread;
+  int top = 1;
+  while ((uint32_t)top < holders) top <<= 1;
+  for (int s = top >> 1; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) {
       Xyzz<CF> o = xyzz_load_shared<CF>(reinterpret_cast<char*>(sm) + (threadIdx.x + s) * 128);
       xyzz_add(acc, o);

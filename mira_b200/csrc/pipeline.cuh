@@ -330,7 +330,8 @@ int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt
   size_t src_stride = a_stride, dst_stride = b_stride;
   uint32_t cnt = n_red;
   while (cnt > 1) {
-    uint32_t per_thread = cnt > 128 * 8 ? 8 : 1;
+    // few points: one per thread (the serial part of a thread is as slow as a tree level, and the GPU is idle anyway)
+    uint32_t per_thread = cnt > ((uint32_t)1 << 16) ? 8 : 1;
     uint32_t per_block = per_thread * 128;
     uint32_t blocks = (cnt + per_block - 1) / per_block;
     k_sum_points<CF><<<dim3(blocks, S), 128, 0, st>>>(src, cnt, per_thread, dst, src_stride, dst_stride);
