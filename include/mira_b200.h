@@ -140,6 +140,13 @@ int mira_msm_set_adaptive_window(mira_msm_ctx *ctx, int enabled);
  * `min_scalars_per_slice` scalars (default 2^19), and slice k+1 crosses PCIe while slice k is accumulated into
  * the same bucket set.  0 disables slicing.  The result does not depend on it. */
 int mira_msm_set_slice_min(mira_msm_ctx *ctx, size_t min_scalars_per_slice);
+/* Slice pipeline: part k+1 of the scalar vector is decomposed into window digits and radix-sorted on a second stream
+ * while part k is accumulated into the (shared) buckets.  Page-locked host-buffer commits always do this with their
+ * H2D slices (mira_msm_set_slice_min); `slices` = 1 turns that off.  Device-resident commits are cut into `slices`
+ * (2..16) equal parts of at least `min_scalars_per_slice` (0 = 2^20) scalars only when asked: measured on B200 the
+ * slicing costs more than the overlap returns, so the default (0) leaves them whole.  The result does
+ * not depend on any of it. */
+int mira_msm_set_pipeline(mira_msm_ctx *ctx, int slices, size_t min_scalars_per_slice);
 /* Experimental, off by default (0): before the XYZZ accumulation, add the entries of every bucket two by two in
  * AFFINE coordinates `levels` times (0..6), each level sharing its inversions by Montgomery's trick
  * (mira_b200/csrc/affine_levels.cuh).  5M + 1S per addition instead of 8M + 2S, but two passes over the gathered

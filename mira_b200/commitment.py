@@ -226,6 +226,11 @@ class CommitmentKey:
         """Host-buffer commits are pipelined in up to 4 slices of >= n scalars behind their H2D copies (0: off)."""
         _check(N.lib().mira_msm_set_slice_min(self._ctx, n))
 
+    def set_pipeline(self, slices: int, min_scalars_per_slice: int = 0):
+        """Slice pipeline (part k+1 sorted on a second stream while part k is accumulated).  Host-buffer commits use it
+        on their H2D slices unless `slices` == 1; device-resident commits only when `slices` >= 2 (default 0: whole)."""
+        _check(N.lib().mira_msm_set_pipeline(self._ctx, slices, min_scalars_per_slice))
+
     def set_affine_levels(self, levels: int):
         """Experimental (default 0): batched-affine pre-reduction levels before the XYZZ accumulation."""
         _check(N.lib().mira_msm_set_affine_levels(self._ctx, levels))

@@ -69,7 +69,16 @@ struct mira_msm_ctx {
   mira_host::Stager stager;                    // pageable host scalars go through page-locked slots (stager.hpp)
   std::vector<mira_host::Table> tables;
   // workspace (grown on demand, reused across commits)
-  mira_host::DevBuf scalars, keys, refs, skeys, srefs, counts, cursor, tile_sums, buckets, part_keys, part_pts, red_a, red_b, result;
+  mira_host::DevBuf scalars, cursor, buckets, part_keys, part_pts, red_a, red_b, result;
+  // Pair-list workspace of one slice: unsorted and sorted (key, ref) arrays, counters, radix-sort scratch.  Two sets, so
+  // that slice k+1 can be decomposed and sorted (prep_stream) while slice k is accumulated (pipeline.cuh).
+  struct SortBufs {
+    mira_host::DevBuf keys, refs, skeys, srefs, counts, tile_sums;
+  } sb[2];
+  cudaStream_t prep_stream = nullptr;          // digits + sort of the next slice, overlapped with the accumulation
+  cudaEvent_t prep_done[2] = {nullptr, nullptr}, acc_done[2] = {nullptr, nullptr}, pipe_start = nullptr;
+  int pipe_slices = -1;                        // device-resident commits: -1 = MIRA_PIPE_SLICES from the environment (default 1 = not sliced)
+  size_t pipe_min_slice = (size_t)1 << 20;     // slices below ~1 M scalars cost more in launches than they hide
   mira_host::DevBuf pa_a, pa_b, pa_work;       // batched-affine levels (affine_levels.cuh): two ping-pong (key, point) lists, scratch
   int affine_levels = -1;                      // -1 = MIRA_AFFINE_LEVELS from the environment (default 0 = off)
   size_t scalars_valid = 0;                    // scalars.p holds the device copy of the last host-buffer commit (this many)

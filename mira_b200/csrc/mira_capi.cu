@@ -120,10 +120,14 @@ void mira_msm_ctx_destroy(mira_msm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& t : ctx->tables) cudaFree(t.d);
-  for (DevBuf* b : {&ctx->scalars, &ctx->keys, &ctx->refs, &ctx->skeys, &ctx->srefs, &ctx->counts, &ctx->cursor, &ctx->tile_sums,
-                    &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->result, &ctx->pa_a, &ctx->pa_b,
-                    &ctx->pa_work})
+  for (DevBuf* b : {&ctx->scalars, &ctx->cursor, &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->result,
+                    &ctx->pa_a, &ctx->pa_b, &ctx->pa_work})
     b->release();
+  for (auto& sb : ctx->sb)
+    for (DevBuf* b : {&sb.keys, &sb.refs, &sb.skeys, &sb.srefs, &sb.counts, &sb.tile_sums}) b->release();
+  for (cudaEvent_t e : {ctx->prep_done[0], ctx->prep_done[1], ctx->acc_done[0], ctx->acc_done[1], ctx->pipe_start})
+    if (e) cudaEventDestroy(e);
+  if (ctx->prep_stream) cudaStreamDestroy(ctx->prep_stream);
   if (ctx->d_bases) cudaFree(ctx->d_bases);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
@@ -259,6 +263,14 @@ int mira_msm_set_adaptive_window(mira_msm_ctx* ctx, int enabled) {
 int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
   ctx->slice_min = min_scalars_per_slice ? min_scalars_per_slice : ~(size_t)0;   // 0 = never slice
+  return MIRA_OK;
+}
+
+int mira_msm_set_pipeline(mira_msm_ctx* ctx, int slices, size_t min_scalars_per_slice) {
+  if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  if (slices < 0 || slices > 16) return fail(MIRA_ERR_INVALID, "pipeline slices %d out of range [0, 16]", slices);
+  ctx->pipe_slices = slices ? slices : -1;
+  ctx->pipe_min_slice = min_scalars_per_slice ? min_scalars_per_slice : (size_t)1 << 20;
   return MIRA_OK;
 }
 

@@ -140,6 +140,12 @@ inline int affine_levels_for(const mira_msm_ctx* ctx) {
 }
 
 struct MsmPlan {
+  struct Prepared {                 // a decomposed and sorted slice, waiting in buffer set `bs` for its accumulation
+    const uint32_t* skeys = nullptr;
+    const uint32_t* srefs = nullptr;
+    uint32_t* d_npairs = nullptr;
+    size_t E = 0;                   // host-side upper bound of *d_npairs
+  } prep[2];
   int affine_levels = 0;
   int c = 0, W = 0;
   Table* tab = nullptr;
@@ -151,7 +157,8 @@ struct MsmPlan {
 };
 
 template <class CF>
-int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan, int n_sets = 1, int window = 0) {
+int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, MsmPlan* plan, int n_sets = 1, int window = 0,
+              int n_bufsets = 1) {
   int rc;
   int c = ctx->forced_window ? ctx->forced_window : (window ? window : choose_window(n));
   Table* tab = nullptr;
@@ -164,32 +171,37 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
     return fail(MIRA_ERR_INVALID, "commit of %d x %zu scalars needs %zu (point, window) pairs: exceeds the 2^31 reference space; shard it",
                 n_sets, n, n * (size_t)W * (size_t)n_sets);
   const size_t bucket_bytes = ((size_t)B + 1) * 128 * (size_t)n_sets;
-  if ((rc = ctx->keys.ensure(E * 4 + 16)) || (rc = ctx->refs.ensure(E * 4 + 16)) || (rc = ctx->skeys.ensure(E * 4 + 16)) ||
-      (rc = ctx->srefs.ensure(E * 4 + 16)) || (rc = ctx->counts.ensure(64)) || (rc = ctx->buckets.ensure(bucket_bytes)) ||
-      (rc = ctx->tile_sums.ensure(radix_sort_temp_bytes(E))))
-    return rc;
+  for (int b = 0; b < n_bufsets; b++) {
+    auto& sb = ctx->sb[b];
+    if ((rc = sb.keys.ensure(E * 4 + 16)) || (rc = sb.refs.ensure(E * 4 + 16)) || (rc = sb.skeys.ensure(E * 4 + 16)) ||
+        (rc = sb.srefs.ensure(E * 4 + 16)) || (rc = sb.counts.ensure(64)) || (rc = sb.tile_sums.ensure(radix_sort_temp_bytes(E))))
+      return rc;
+  }
+  if ((rc = ctx->buckets.ensure(bucket_bytes))) return rc;
   CU(cudaMemsetAsync(ctx->buckets.p, 0, bucket_bytes, st));
   plan->c = c; plan->W = W; plan->tab = tab; plan->B = B; plan->max_slice = max_slice; plan->n_sets = n_sets;
   plan->launches = 0; plan->entries = 0;
   return MIRA_OK;
 }
 
+// First half of a slice: scalars [first, first + n) -> sorted (bucket, point reference) pairs in buffer set `bs`.
 template <class CF, class SF>
-int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets, size_t first, size_t n, bool add_mode,
-              cudaStream_t st, PhaseTimer* pt) {
+int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets, size_t first, size_t n, bool add_mode, int bs,
+             cudaStream_t st, PhaseTimer* pt) {
   int rc;
   const int c = plan->c, W = plan->W;
   Table* tab = plan->tab;
+  auto& sb = ctx->sb[bs];
   const size_t E = n * (size_t)W * (size_t)plan->n_sets;
-  uint32_t* d_npairs = (uint32_t*)ctx->counts.p;     // number of (bucket, ref) pairs, produced on the device
+  uint32_t* d_npairs = (uint32_t*)sb.counts.p;     // number of (bucket, ref) pairs, produced on the device
   if (pt) pt->mark(0);
   // ---- digits (compacted pair list)
   CU(cudaMemsetAsync(d_npairs, 0, 4, st));
-  if (!add_mode) CU(cudaMemsetAsync((char*)ctx->counts.p + 48, 0, 8, st));      // affine additions of this commit
+  if (!add_mode) CU(cudaMemsetAsync((char*)sb.counts.p + 48, 0, 8, st));      // affine additions of this commit
   for (int s = 0; s < plan->n_sets; s++) {
     k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
-        d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), (uint32_t*)ctx->keys.p,
-        (uint32_t*)ctx->refs.p, d_npairs);
+        d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), (uint32_t*)sb.keys.p,
+        (uint32_t*)sb.refs.p, d_npairs);
     plan->launches++;
   }
   if (pt) pt->mark(1);
@@ -197,12 +209,27 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
   int in_b = 0;
   int key_bits = c;          // keys are < n_sets * (B + 1)
   while (((uint64_t)1 << key_bits) < (uint64_t)plan->n_sets * (plan->B + 1)) key_bits++;
-  if ((rc = radix_sort_pairs((uint32_t*)ctx->keys.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->skeys.p, (uint32_t*)ctx->srefs.p, d_npairs, E,
-                             key_bits, ctx->tile_sums.p, st, &in_b, &plan->launches)))
+  if ((rc = radix_sort_pairs((uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, d_npairs, E,
+                             key_bits, sb.tile_sums.p, st, &in_b, &plan->launches)))
     return rc;
-  const uint32_t* skeys = (const uint32_t*)(in_b ? ctx->skeys.p : ctx->keys.p);
-  const uint32_t* srefs = (const uint32_t*)(in_b ? ctx->srefs.p : ctx->refs.p);
+  plan->prep[bs].skeys = (const uint32_t*)(in_b ? sb.skeys.p : sb.keys.p);
+  plan->prep[bs].srefs = (const uint32_t*)(in_b ? sb.srefs.p : sb.refs.p);
+  plan->prep[bs].d_npairs = d_npairs;
+  plan->prep[bs].E = E;
   if (pt) pt->mark(2);
+  return MIRA_OK;
+}
+
+// Second half: the sorted pairs of buffer set `bs` are added into the buckets (add_mode: on top of earlier slices).
+template <class CF>
+int msm_acc(mira_msm_ctx* ctx, MsmPlan* plan, bool add_mode, int bs, cudaStream_t st, PhaseTimer* pt) {
+  int rc;
+  Table* tab = plan->tab;
+  auto& sb = ctx->sb[bs];
+  const uint32_t* skeys = plan->prep[bs].skeys;
+  const uint32_t* srefs = plan->prep[bs].srefs;
+  uint32_t* d_npairs = plan->prep[bs].d_npairs;
+  const size_t E = plan->prep[bs].E;
   // ---- batched-affine levels: add the entries of every bucket two by two while the list is long (affine_levels.cuh)
   const uint32_t* acc_keys = skeys;
   const uint32_t* acc_refs = srefs;
@@ -232,8 +259,8 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
       else if ((rc = ctx->pa_a.ensure(need_a)) || (rc = ctx->pa_b.ensure(need_b)) || (rc = ctx->pa_work.ensure(need_w)))
         return rc;
     }
-    uint32_t* d_counts = (uint32_t*)ctx->counts.p;             // [0] pairs, [1 + l] list length after level l
-    unsigned long long* d_adds = (unsigned long long*)((char*)ctx->counts.p + 48);
+    uint32_t* d_counts = (uint32_t*)sb.counts.p;               // [0] pairs, [1 + l] list length after level l
+    unsigned long long* d_adds = (unsigned long long*)((char*)sb.counts.p + 48);
     for (int l = 0; l < levels; l++) {
       const unsigned tiles = (unsigned)((bound[l] + PA_TILE - 1) / PA_TILE);
       const size_t threads = (size_t)tiles * PA_THREADS;
@@ -308,6 +335,65 @@ int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets
   return MIRA_OK;
 }
 
+// One slice on one stream (batched commits, profiled commits, small commits).
+template <class CF, class SF>
+int msm_slice(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets, size_t first, size_t n, bool add_mode,
+              cudaStream_t st, PhaseTimer* pt) {
+  int rc;
+  if ((rc = msm_prep<CF, SF>(ctx, plan, d_scalar_sets, first, n, add_mode, 0, st, pt))) return rc;
+  return msm_acc<CF>(ctx, plan, add_mode, 0, st, pt);
+}
+
+// Software pipeline over slices: the digits and the sort of slice k+1 run on ctx->prep_stream while slice k is
+// accumulated on `st`.  The two are complementary on paper — the sort is latency/bandwidth-bound on the ALU and LSU
+// pipes, the accumulation integer-multiply-bound with 11 % of the DRAM bandwidth — and two INDEPENDENT commits do
+// overlap that way (tools/overlap_probe.py: 42.9 -> 39.8 ms per pair of 2^23-point commits).  Inside one commit the
+// slices pay for it: every later slice spends one extra mixed addition per non-empty bucket, and the 512-thread sort
+// blocks only get onto an SM when several accumulation blocks have retired.  Measured at 2^24 points, device-resident:
+// 1 slice 39.9 ms, 2 slices 40.5-41.2, 4 slices 41.6-42.9 (low / high priority prep stream), 8 slices 44.4.  So a
+// device-resident commit is NOT sliced by default (mira_msm_set_pipeline turns it on); a page-locked host-buffer
+// commit, which is cut into H2D slices anyway, does overlap the preparation of slice k+1 with the accumulation of
+// slice k (2^24: 41.96 -> 41.47 ms end to end).  `ready[k]`, if given, is an event the preparation of slice k has to
+// wait for (the H2D copy).
+inline int pipe_slices_for(const mira_msm_ctx* ctx, size_t n) {
+  static const int env = [] { const char* e = getenv("MIRA_PIPE_SLICES"); return e ? atoi(e) : 1; }();
+  int k = ctx->pipe_slices > 0 ? ctx->pipe_slices : env;
+  if (k < 1) k = 1;
+  if (k > 16) k = 16;
+  while (k > 1 && n / (size_t)k < ctx->pipe_min_slice) k--;
+  return k;
+}
+inline int pipe_setup(mira_msm_ctx* ctx) {
+  if (!ctx->prep_stream) {
+    CU(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+  }
+  for (cudaEvent_t* e : {&ctx->prep_done[0], &ctx->prep_done[1], &ctx->acc_done[0], &ctx->acc_done[1], &ctx->pipe_start})
+    if (!*e) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  return MIRA_OK;
+}
+template <class CF, class SF>
+int msm_pipeline(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, const size_t* bounds, int n_slices, cudaEvent_t* ready,
+                 cudaStream_t st) {
+  int rc;
+  if ((rc = pipe_setup(ctx))) return rc;
+  // the preparation must not start before work already queued on `st` (it may produce the scalars) has finished
+  CU(cudaEventRecord(ctx->pipe_start, st));
+  CU(cudaStreamWaitEvent(ctx->prep_stream, ctx->pipe_start, 0));
+  for (int k = 0; k < n_slices; k++) {
+    const int bs = k & 1;
+    const size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
+    if (ready) CU(cudaStreamWaitEvent(ctx->prep_stream, ready[k], 0));
+    if (k >= 2) CU(cudaStreamWaitEvent(ctx->prep_stream, ctx->acc_done[bs], 0));     // buffer set free again
+    const void* sets[1] = {(const char*)d_scalars + first * 32};
+    if ((rc = msm_prep<CF, SF>(ctx, plan, sets, first, cnt, k > 0, bs, ctx->prep_stream, nullptr))) return rc;
+    CU(cudaEventRecord(ctx->prep_done[bs], ctx->prep_stream));
+    CU(cudaStreamWaitEvent(st, ctx->prep_done[bs], 0));
+    if ((rc = msm_acc<CF>(ctx, plan, k > 0, bs, st, nullptr))) return rc;
+    CU(cudaEventRecord(ctx->acc_done[bs], st));
+  }
+  return MIRA_OK;
+}
+
 template <class CF>
 int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt) {
   int rc;
@@ -366,6 +452,18 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
   int window = 0;
   if ((rc = pick_window<SF>(ctx, d_scalars, n, true, st, &window))) return rc;
   PhaseTimer pt(ctx->profiling, st);
+  // profiled commits and commits with affine levels run their phases one after the other (the phase times are what
+  // the profile is for); everything else of sufficient length is software-pipelined over equal slices
+  const int K = (ctx->profiling || affine_levels_for(ctx) > 0) ? 1 : pipe_slices_for(ctx, n);
+  if (K > 1) {
+    size_t bounds[17];
+    for (int k = 0; k <= K; k++) bounds[k] = k == K ? n : ((n / (size_t)K * (size_t)k) & ~(size_t)255);
+    size_t max_slice = 0;
+    for (int k = 0; k < K; k++) max_slice = std::max(max_slice, bounds[k + 1] - bounds[k]);
+    if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan, 1, window, 2))) return rc;
+    if ((rc = msm_pipeline<CF, SF>(ctx, &plan, d_scalars, bounds, K, nullptr, st))) return rc;
+    return msm_finish<CF>(ctx, &plan, st, nullptr);
+  }
   if ((rc = msm_begin<CF>(ctx, n, n, st, &plan, 1, window))) return rc;
   const void* sets[1] = {d_scalars};
   if ((rc = msm_slice<CF, SF>(ctx, &plan, sets, 0, n, false, st, &pt))) return rc;
@@ -452,7 +550,14 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
       CU(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
     }
   MsmPlan plan;
-  if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan, 1, window))) return rc;
+  const bool overlap = n_slices > 1 && affine_levels_for(ctx) == 0 && ctx->pipe_slices != 1;      // set_pipeline(1) turns it off
+  if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan, 1, window, overlap ? 2 : 1))) return rc;
+  if (overlap && !pageable) {
+    // every copy is already queued: slice k+1 is decomposed and sorted behind its copy while slice k is accumulated
+    if ((rc = msm_pipeline<CF, SF>(ctx, &plan, ctx->scalars.p, bounds, n_slices, ctx->copy_done, st))) return rc;
+    ctx->scalars_valid = n;
+    return msm_finish<CF>(ctx, &plan, st, nullptr);
+  }
   for (int k = 0; k < n_slices; k++) {
     size_t first = bounds[k], cnt = bounds[k + 1] - bounds[k];
     if (pageable) {

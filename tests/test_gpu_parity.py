@@ -388,6 +388,7 @@ def test_randomized_commit_configurations(gpu):
         ck.set_slice_min(rng.choice([0, 1, 50, 1 << 19]))
         ck.set_adaptive_window(rng.random() < 0.5)
         ck.set_affine_levels(rng.choice([0, 0, 1, 2, 4, 6]))
+        ck.set_pipeline(rng.choice([0, 1, 2, 3, 4, 7, 16]), rng.choice([0, 1, 100, 5000]))
         want = O.commit(curve, bases, sc)
         src = rng.choice(["bytes", "pinned", "device"])
         if src == "bytes":
@@ -521,3 +522,31 @@ def test_reference_lagrange_kat_on_the_gpu(gpu):
         got.append(int.from_bytes(op(TO_CANON, v), "little"))
         wi = op(MUL, wi, w)
     assert got == want
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_pipelined_commit_equals_unpipelined(gpu, curve):
+    """The slice pipeline (digits + sort of part k+1 on a second stream while part k is accumulated) only changes speed:
+    every slice count gives the oracle's bytes, for device and for page-locked host scalars, uniform and witness-like,
+    back to back on the same context (buffer sets and events are reused), and through the asynchronous partial path."""
+    from mira_b200 import CommitmentKey, combine_partials_device
+    n = 70_001
+    bases = O.gen_bases(curve, 661, n)
+    ck = CommitmentKey(curve, bases)
+    for dist in (0, 1):
+        sc = O.gen_scalars(curve, 662 + dist, n, dist)
+        want = O.commit(curve, bases, sc)
+        d = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
+        pinned = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
+        for slices, min_slice in ((1, 0), (2, 1), (4, 1000), (16, 1), (5, 3000), (0, 0)):
+            ck.set_pipeline(slices, min_slice)
+            ck.set_slice_min(4000)                       # host path: H2D slices, pipelined as well
+            for _ in range(2):
+                assert ck.commit_device(d.data_ptr(), n) == want, (slices, min_slice, dist)
+                assert ck.commit(pinned) == want, (slices, min_slice, dist, "pinned")
+            assert ck.commit(sc) == want                 # pageable source: staged, not pipelined
+            out = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            ck.partial_batch_device([d.data_ptr()], n, out.data_ptr())
+            ck.partial_batch_device([d.data_ptr()], n, out.data_ptr())     # queued twice without a host sync in between
+            torch.cuda.synchronize()
+            assert combine_partials_device(curve, out.data_ptr(), 1, 1, 128) == [want]
