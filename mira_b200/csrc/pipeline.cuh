@@ -454,10 +454,18 @@ int msm_device(mira_msm_ctx* ctx, const void* d_scalars, size_t n, cudaStream_t 
   PhaseTimer pt(ctx->profiling, st);
   // profiled commits and commits with affine levels run their phases one after the other (the phase times are what
   // the profile is for); everything else of sufficient length is software-pipelined over equal slices
-  const int K = (ctx->profiling || affine_levels_for(ctx) > 0) ? 1 : pipe_slices_for(ctx, n);
+  int K = (ctx->profiling || affine_levels_for(ctx) > 0) ? 1 : pipe_slices_for(ctx, n);
+  size_t bounds[17];
+  if (K > 1) {              // equal parts on 256-scalar boundaries; parts that round to nothing are dropped
+    int parts = 0;
+    bounds[0] = 0;
+    for (int k = 1; k <= K; k++) {
+      size_t b = k == K ? n : ((n / (size_t)K * (size_t)k) & ~(size_t)255);
+      if (b > bounds[parts]) bounds[++parts] = b;
+    }
+    K = parts;
+  }
   if (K > 1) {
-    size_t bounds[17];
-    for (int k = 0; k <= K; k++) bounds[k] = k == K ? n : ((n / (size_t)K * (size_t)k) & ~(size_t)255);
     size_t max_slice = 0;
     for (int k = 0; k < K; k++) max_slice = std::max(max_slice, bounds[k + 1] - bounds[k]);
     if ((rc = msm_begin<CF>(ctx, n, max_slice, st, &plan, 1, window, 2))) return rc;
