@@ -110,7 +110,7 @@ def test_index_errors_match_the_reference(W):
 
 
 @pytest.mark.parametrize("field,m", [(FR, R.R_), (FQ, R.P)])
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MIRA_EXPR_SEEDS", "4"))))      # raise for a soak run
 def test_random_expressions(W, field, m, seed):
     rng = random.Random(200 + seed)
     n_sel, n_fix, n_adv, n_ch = 2, 3, 4, 3
@@ -346,8 +346,9 @@ def test_row_range_shards_concatenate_to_the_whole(W):
 
 # ---- lookup argument: SPS rounds 2 / 3 (src/plonk/mod.rs:748-907, src/plonk/lookup.rs:212-319)
 @pytest.mark.parametrize("field,curve,m", [(FR, R.BN254, R.R_), (FQ, R.GRUMPKIN, R.P)])
-def test_lookup_m_and_h_g(W, field, curve, m):
-    rng = random.Random(21)
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MIRA_LOOKUP_SEEDS", "1"))))      # raise for a soak run
+def test_lookup_m_and_h_g(W, field, curve, m, seed):
+    rng = random.Random(21 + seed)
     for n_l, n_t in ((1, 1), (300, 64), (5000, 4096), (70_000, 1 << 15)):
         table = [rng.randrange(m) for _ in range(max(n_t - 6, 1))]
         t = (table + [0, 1, m - 1, table[0], table[-1], table[-1]])[:n_t]
