@@ -3,6 +3,7 @@ dead-code removal, liveness-based slot allocation): the linked device program is
 `mira_test_eval_link` hook and SIMULATED here in Python with big integers, then compared with the oracle's
 evaluation of the original program.  No compute entry point of the library is called (no GPU here)."""
 import ctypes as C
+import os
 import random
 
 import pytest
@@ -121,7 +122,7 @@ def link_and_simulate(ge: G.GraphEvaluator, d: Domain):
     return rc, (outs[0] if outs else None), st
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MIRA_EXPR_SEEDS", "8"))))      # raise for a soak run
 def test_linked_random_programs_match_oracle(seed):
     rng = random.Random(300 + seed)
     d = Domain(M, 6, 2, 3, 4, 0, 1, 3, seed=seed, sparse=(seed % 2 == 0))
