@@ -52,3 +52,22 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for p in pats:
                     assert not re.search(p, txt), (os.path.join(dirpath, f), p)
+
+
+def test_rust_bindings_are_current_and_complete():
+    """bindings/mira_b200_sys.rs (the `extern "C"` block of the Rust -sys crate) is generated from the
+    header: the committed file must be what the generator emits now, and must declare exactly the exported symbols."""
+    import sys
+    from mira_b200 import _native as N
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_bindings as g
+    with open(g.OUT) as f:
+        committed = f.read()
+    assert committed == g.generate(), "run `python tools/gen_rust_bindings.py`"
+    declared = set(re.findall(r"pub fn (mira_\w+)\(", committed))
+    assert declared == set(N.SYMBOLS)
+    # a few signatures spelled out, so that a parser regression cannot hide behind the self-comparison above
+    assert "pub fn mira_msm_commit(ctx: *mut mira_msm_ctx, scalars: *const c_void, n: usize, out_affine: *mut c_void) -> c_int;" in committed
+    assert "pub fn mira_msm_ctx_create(curve: c_int, bases: *const c_void, n_bases: usize, bases_on_device: c_int, device: c_int, out: *mut *mut mira_msm_ctx) -> c_int;" in committed
+    assert "outs_dev: *const *mut c_void" in committed and "pub selectors: *const *const c_void," in committed
+    assert "pub fn mira_msm_ctx_destroy(ctx: *mut mira_msm_ctx);" in committed
