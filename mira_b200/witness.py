@@ -14,7 +14,7 @@ memory only; every computation is a kernel in libmira_b200.so.  There is no CPU 
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 from . import _native as N
 
