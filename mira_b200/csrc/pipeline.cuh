@@ -94,8 +94,10 @@ constexpr int MAX_BATCH = 32;
 constexpr size_t ADAPT_MIN_N = (size_t)1 << 18;
 constexpr uint32_t ADAPT_CHUNKS = 64, ADAPT_CHUNK_LEN = 128;
 template <class SF>
-int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device, cudaStream_t st, int* window) {
+int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device, cudaStream_t st, int* window,
+                double* pairs_per_scalar = nullptr) {
   *window = 0;
+  if (pairs_per_scalar) *pairs_per_scalar = 0.0;        // 0 = not sampled
   if (ctx->forced_window || !ctx->adaptive_window || n < ADAPT_MIN_N) return MIRA_OK;
   int rc;
   const size_t samples = (size_t)ADAPT_CHUNKS * ADAPT_CHUNK_LEN, stride = n / ADAPT_CHUNKS;
@@ -122,6 +124,11 @@ int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device
   for (auto& t : ctx->tables)
     if (t.c >= 6 && t.c <= 24 && t.n_cover >= n && costs[t.c] <= 1.05 * costs[best] && (!keep || costs[t.c] < costs[keep])) keep = t.c;
   *window = keep ? keep : best;
+  if (pairs_per_scalar) {       // non-zero signed digits per scalar the sample predicts for the chosen window
+    double pairs = 0;
+    for (int L = 1; L <= 256; L++) pairs += (double)ctx->h_hist[L] * (double)((L + *window - 1) / *window);
+    *pairs_per_scalar = pairs / (double)samples;
+  }
   return MIRA_OK;
 }
 
@@ -503,14 +510,27 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   }
   ctx->scalars_valid = 0;
   if ((rc = ctx->scalars.ensure(n * 32))) return rc;
-  // Slice sizes grow geometrically (1 : 4 : 16 : 64): accumulating a slice takes ~4x as long as copying it, so every
-  // copy but the first hides behind the previous slice's compute and the exposed first copy is as small as
-  // ctx->slice_min allows (2^24 scalars: 3 slices, 0.8 M first => ~0.5 ms of the 9.7 ms H2D stays visible).
+  // sampled BEFORE the slice copies are queued (its 64 small copies must not wait behind them); also tells how dense
+  // the vector is, i.e. how much accumulation time a copied scalar buys
+  int window = 0;
+  double pairs_per_scalar = 0.0;
+  if ((rc = pick_window<SF>(ctx, h_scalars, n, false, st, &window, &pairs_per_scalar))) return rc;
+  // Slice sizes grow geometrically: slice k+1 crosses PCIe while slice k is accumulated, so it may be as much larger
+  // as accumulating a scalar takes longer than copying it.  Uniform scalars (~12 pairs each at 2^24): ~4x, hence
+  // 1 : 4 : 16 — the exposed first copy is then as small as ctx->slice_min allows (2^24 scalars: 0.8 M first =>
+  // ~0.5 ms of the 9.7 ms H2D stays visible).  Witness columns are sparse (~1 pair per scalar): their accumulation is
+  // no longer than their copy, a 4x slice would wait for its own copy, and equal slices are right (the commit is then
+  // copy-bound and ends one slice's accumulation after the last copy).
+  size_t growth = 4;
+  if (pairs_per_scalar > 0.0) {
+    const double ratio = pairs_per_scalar * 0.2 / 0.58;      // ~0.2 ns per pair (digits, sort, accumulate) vs 32 B at ~55 GB/s
+    growth = ratio >= 3.0 ? 4 : (ratio >= 1.5 ? 2 : 1);
+  }
   int K = 1;
   {
     size_t weight = 1, sum = 1;
-    while (K < SLICE_MAX_COUNT && ctx->slice_min && n / (sum + weight * 4) >= ctx->slice_min) {
-      weight *= 4;
+    while (K < SLICE_MAX_COUNT && ctx->slice_min && n / (sum + weight * growth) >= ctx->slice_min) {
+      weight *= growth;
       sum += weight;
       K++;
     }
@@ -520,10 +540,10 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   bounds[0] = 0;
   {
     size_t total_w = 0, w = 1;
-    for (int k = 0; k < K; k++, w *= 4) total_w += w;
+    for (int k = 0; k < K; k++, w *= growth) total_w += w;
     size_t pos = 0;
     w = 1;
-    for (int k = 0; k < K - 1; k++, w *= 4) {
+    for (int k = 0; k < K - 1; k++, w *= growth) {
       size_t len = ((n * w / total_w) + 255) & ~(size_t)255;
       if (pos + len >= n) break;
       pos += len;
@@ -543,8 +563,6 @@ int msm_host(mira_msm_ctx* ctx, const void* h_scalars, size_t n, cudaStream_t st
   // page-locked source: all copies are queued now and run by the copy engine on their own;
   // pageable source (a plain Rust Vec): each slice is staged through page-locked slots by worker threads right
   // before its compute is queued, so the staging of slice k+1 overlaps the accumulation of slice k
-  int window = 0;        // sampled BEFORE the slice copies are queued: its 64 small copies must not wait behind them
-  if ((rc = pick_window<SF>(ctx, h_scalars, n, false, st, &window))) return rc;
   cudaPointerAttributes attr{};
   bool pageable = true;
   if (cudaPointerGetAttributes(&attr, h_scalars) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
