@@ -58,8 +58,15 @@ size_t mira_msm_ctx_len(const mira_msm_ctx *ctx);
  * Returns MIRA_OK or MIRA_ERR_NOT_ON_CURVE. */
 int mira_msm_ctx_check_on_curve(mira_msm_ctx *ctx);
 /* Build (or fetch) the fixed-base table that commits of length `n` will use, so that the first timed
- * commit does not pay for it.  Optional. */
+ * commit does not pay for it.  Optional.  The table cache is bounded: tables are only built while 6 GiB of device
+ * memory stay free beside them, least-recently-used ones are evicted to make room, and a commit whose table cannot
+ * be built falls back to the cached table covering n with the closest window (the result never depends on it). */
 int mira_msm_ctx_prepare(mira_msm_ctx *ctx, size_t n);
+/* The same for vectors that LOOK LIKE `scalars` (n x 32 B, host or device): the adaptive window (see
+ * mira_msm_set_adaptive_window) is chosen from a sample of them, exactly as a commit of that vector would, and that
+ * table is built -- mira_msm_ctx_prepare(n) builds the one uniform scalars use, which sparse witness columns never
+ * touch. */
+int mira_msm_ctx_prepare_for(mira_msm_ctx *ctx, const void *scalars, size_t n, int scalars_on_device);
 
 /* ---- CommitmentKey::commit (src/commitment.rs:78-87) --------------------------------------------
  * out_affine (HOST, 64 B) = to_affine( sum_{i<n} scalars[i] * bases[i] ); identity -> 64 zero bytes.
@@ -72,8 +79,12 @@ int mira_msm_commit(mira_msm_ctx *ctx, const void *scalars, size_t n, void *out_
  * H2D copy (run_sps_protocol then commit_cross_terms then fold, src/nifs/vanilla/mod.rs:220-251). */
 const void *mira_msm_scalars_device(const mira_msm_ctx *ctx, size_t *n_out);
 /* Same, with `scalars` already resident on the context's device (e.g. produced by the cross-term
- * kernels); `stream` is a cudaStream_t (NULL = the context's own stream).  The result is still
- * returned to the host because every caller hashes it (src/poseidon/poseidon_hash.rs:129-143). */
+ * kernels); `stream` is a cudaStream_t, NULL = the legacy default stream -- the SAME convention as the witness
+ * kernels below, so mira_fold_w(..., NULL) followed by mira_msm_commit_device(..., NULL) is ordered.  (This holds
+ * for every entry point that reads device scalars: commit_device, commit_batch, partial with scalars_on_device,
+ * partial_batch_dev.  Host-buffer commits run on the context's private stream.)  A fixed-base table built lazily by
+ * the call is built on `stream` too.  The result is still returned to the host because every caller hashes it
+ * (src/poseidon/poseidon_hash.rs:129-143). */
 int mira_msm_commit_device(mira_msm_ctx *ctx, const void *scalars_dev, size_t n, void *out_affine, void *stream);
 
 /* `cross_terms.iter().map(|v| ck.commit(v))` (src/nifs/vanilla/mod.rs:124-127) as ONE call: `count` (<= 32)

@@ -26,7 +26,7 @@ MIRA_EVAL_LOOKUP_DOMAIN = 1
 # every symbol include/mira_b200.h declares (tests/test_capi_symbols.py checks the .so exports them all)
 SYMBOLS = [
     "mira_last_error", "mira_msm_ctx_create", "mira_msm_ctx_destroy", "mira_msm_ctx_len",
-    "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_commit", "mira_msm_commit_device", "mira_msm_commit_batch", "mira_msm_scalars_device",
+    "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_ctx_prepare_for", "mira_msm_commit", "mira_msm_commit_device", "mira_msm_commit_batch", "mira_msm_scalars_device",
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_msm_set_adaptive_window", "mira_msm_set_slice_min", "mira_msm_set_affine_levels", "mira_msm_set_pipeline", "mira_msm_partial_batch_dev", "mira_msm_combine_dev", "mira_host_register", "mira_host_unregister", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
@@ -84,6 +84,7 @@ def lib():
     L.mira_msm_ctx_len.restype = sz
     L.mira_msm_ctx_check_on_curve.argtypes = [vp]
     L.mira_msm_ctx_prepare.argtypes = [vp, sz]
+    L.mira_msm_ctx_prepare_for.argtypes = [vp, vp, sz, i]
     L.mira_msm_commit.argtypes = [vp, vp, sz, vp]
     L.mira_msm_commit_device.argtypes = [vp, vp, sz, vp, vp]
     L.mira_msm_scalars_device.argtypes = [vp, C.POINTER(sz)]

@@ -158,9 +158,15 @@ class CommitmentKey:
     def check_on_curve(self):
         _check(N.lib().mira_msm_ctx_check_on_curve(self._ctx))
 
-    def prepare(self, n: int):
-        """Build the fixed-base table commits of length n use (otherwise built lazily on first commit)."""
-        _check(N.lib().mira_msm_ctx_prepare(self._ctx, n), n, self._n)
+    def prepare(self, n: int, like=None, like_on_device: bool = False):
+        """Build the fixed-base table commits of length n use (otherwise built lazily on first commit).  `like`: a
+        vector (host buffer, or device pointer with like_on_device) whose sampled density picks the window, as a
+        commit of it would (sparse witness columns use a much narrower window than uniform scalars)."""
+        if like is None:
+            _check(N.lib().mira_msm_ctx_prepare(self._ctx, n), n, self._n)
+            return
+        ptr = like if like_on_device else _as_ptr(like)[0]
+        _check(N.lib().mira_msm_ctx_prepare_for(self._ctx, ptr, n, 1 if like_on_device else 0), n, self._n)
 
     def commit_device(self, scalars_dev_ptr: int, n: int, stream: int = 0) -> bytes:
         out = C.create_string_buffer(POINT_BYTES)

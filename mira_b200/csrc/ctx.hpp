@@ -49,6 +49,8 @@ struct Table {
   int c = 0, W = 0;
   uint32_t n_cover = 0;
   void* d = nullptr;
+  size_t bytes = 0;
+  uint64_t last_use = 0;      // ctx->table_clock at the last commit that used it (LRU eviction under memory pressure)
 };
 
 inline int windows_for(int c) { return (255 + c - 1) / c; }
@@ -68,6 +70,7 @@ struct mira_msm_ctx {
   cudaEvent_t compute_idle = nullptr;
   mira_host::Stager stager;                    // pageable host scalars go through page-locked slots (stager.hpp)
   std::vector<mira_host::Table> tables;
+  uint64_t table_clock = 0;
   // workspace (grown on demand, reused across commits)
   mira_host::DevBuf scalars, cursor, buckets, part_keys, part_pts, red_a, red_b, result;
   // Pair-list workspace of one slice: unsorted and sorted (key, ref) arrays, counters, radix-sort scratch.  Two sets, so
@@ -99,7 +102,7 @@ namespace mira_host {
 struct CurveOps {
   int (*commit)(mira_msm_ctx*, const void* scalars, size_t n, int on_device, void* out, bool want_affine, cudaStream_t st);
   int (*commit_batch)(mira_msm_ctx*, const void* const* scalar_sets_dev, size_t count, size_t n, void* out, cudaStream_t st);
-  int (*prepare)(mira_msm_ctx*, size_t n);
+  int (*prepare)(mira_msm_ctx*, size_t n, const void* like_scalars, int on_device);
   int (*check_on_curve)(mira_msm_ctx*);
   int (*combine)(const void* partials_host, size_t count, void* out_affine_host);
   int (*partial_batch_dev)(mira_msm_ctx*, const void* const* scalar_sets_dev, size_t count, size_t n, void* out_xyzz_dev, cudaStream_t st);

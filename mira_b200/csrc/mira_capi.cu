@@ -63,14 +63,21 @@ int choose_window_sampled(size_t n, const uint32_t* hist, size_t samples, double
 
 static int valid_curve(int curve) { return curve == MIRA_BN254_G1 || curve == MIRA_GRUMPKIN_G1; }
 
+// Stream convention (include/mira_b200.h): entry points that read DEVICE scalars run on the caller's stream, and NULL
+// there is the legacy default stream, exactly as for the witness kernels (mira_fold_w, mira_eval_rows, ...), so that
+// `mira_fold_w(..., NULL)` followed by `mira_msm_commit_device(..., NULL)` is ordered.  Host-buffer commits have no
+// device-side producer and run on the context's own non-blocking stream.
+static cudaStream_t stream_for(mira_msm_ctx* ctx, int scalars_on_device, void* stream) {
+  return scalars_on_device ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : ctx->stream);
+}
+
 static int dispatch_commit(mira_msm_ctx* ctx, const void* scalars, size_t n, int on_device, void* out, bool want_affine, void* stream) {
   if (!ctx || !out || (n && !scalars)) return fail(MIRA_ERR_INVALID, "null argument");
   if (n > ctx->n_bases)   // src/commitment.rs:79-86: checked before any arithmetic
     return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return ops_for(ctx->curve).commit(ctx, scalars, n, on_device, out, want_affine, st);
+  return ops_for(ctx->curve).commit(ctx, scalars, n, on_device, out, want_affine, stream_for(ctx, on_device, stream));
 }
 
 }  // namespace mira_host
@@ -156,7 +163,16 @@ int mira_msm_ctx_prepare(mira_msm_ctx* ctx, size_t n) {
   if (n == 0) return MIRA_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  return ops_for(ctx->curve).prepare(ctx, n);
+  return ops_for(ctx->curve).prepare(ctx, n, nullptr, 0);
+}
+
+int mira_msm_ctx_prepare_for(mira_msm_ctx* ctx, const void* scalars, size_t n, int scalars_on_device) {
+  if (!ctx || (n && !scalars)) return fail(MIRA_ERR_INVALID, "null argument");
+  if (n > ctx->n_bases) return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
+  if (n == 0) return MIRA_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  return ops_for(ctx->curve).prepare(ctx, n, scalars, scalars_on_device);
 }
 
 int mira_msm_commit(mira_msm_ctx* ctx, const void* scalars, size_t n, void* out_affine) {
@@ -179,8 +195,7 @@ int mira_msm_commit_batch(mira_msm_ctx* ctx, const void* const* scalars_dev, siz
   if (!count) return MIRA_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return ops_for(ctx->curve).commit_batch(ctx, scalars_dev, count, n, out_affine, st);
+  return ops_for(ctx->curve).commit_batch(ctx, scalars_dev, count, n, out_affine, stream_for(ctx, 1, stream));
 }
 
 int mira_msm_combine(int curve, const void* partials, size_t count, int device, void* out_affine) {
@@ -200,8 +215,7 @@ int mira_msm_partial_batch_dev(mira_msm_ctx* ctx, const void* const* scalars_dev
   if (!count) return MIRA_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return ops_for(ctx->curve).partial_batch_dev(ctx, scalars_dev, count, n, out_xyzz_dev, st);
+  return ops_for(ctx->curve).partial_batch_dev(ctx, scalars_dev, count, n, out_xyzz_dev, stream_for(ctx, 1, stream));
 }
 
 int mira_msm_combine_dev(int curve, const void* partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride, int device,
@@ -216,16 +230,19 @@ int mira_msm_combine_dev(int curve, const void* partials_dev, size_t n_ranks, si
 
 int mira_msm_get_stats(const mira_msm_ctx* ctx, mira_msm_stats* out) {
   if (!ctx || !out) return fail(MIRA_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(const_cast<mira_msm_ctx*>(ctx)->mu);
   *out = ctx->stats;
   return MIRA_OK;
 }
 int mira_msm_set_profiling(mira_msm_ctx* ctx, int enabled) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->profiling = enabled != 0;
   return MIRA_OK;
 }
 int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
   if (window_bits != 0 && (window_bits < 2 || window_bits > 26)) return fail(MIRA_ERR_INVALID, "window must be 0 or in [2, 26]");
   ctx->forced_window = window_bits;
   return MIRA_OK;
@@ -233,6 +250,7 @@ int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
 
 const void* mira_msm_scalars_device(const mira_msm_ctx* ctx, size_t* n_out) {
   if (!ctx) return nullptr;
+  std::lock_guard<std::mutex> lk(const_cast<mira_msm_ctx*>(ctx)->mu);
   if (n_out) *n_out = ctx->scalars_valid;
   return ctx->scalars_valid ? ctx->scalars.p : nullptr;
 }
@@ -256,18 +274,21 @@ int mira_host_unregister(void* host_ptr) {
 
 int mira_msm_set_adaptive_window(mira_msm_ctx* ctx, int enabled) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->adaptive_window = enabled != 0;
   return MIRA_OK;
 }
 
 int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->slice_min = min_scalars_per_slice ? min_scalars_per_slice : ~(size_t)0;   // 0 = never slice
   return MIRA_OK;
 }
 
 int mira_msm_set_pipeline(mira_msm_ctx* ctx, int slices, size_t min_scalars_per_slice) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
   if (slices < 0 || slices > 16) return fail(MIRA_ERR_INVALID, "pipeline slices %d out of range [0, 16]", slices);
   ctx->pipe_slices = slices ? slices : -1;
   ctx->pipe_min_slice = min_scalars_per_slice ? min_scalars_per_slice : (size_t)1 << 20;
@@ -276,6 +297,7 @@ int mira_msm_set_pipeline(mira_msm_ctx* ctx, int slices, size_t min_scalars_per_
 
 int mira_msm_set_affine_levels(mira_msm_ctx* ctx, int levels) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
   if (levels < 0 || levels > 6) return fail(MIRA_ERR_INVALID, "affine levels %d out of range [0, 6]", levels);
   ctx->affine_levels = levels;
   return MIRA_OK;

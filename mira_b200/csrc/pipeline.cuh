@@ -11,15 +11,20 @@
 namespace mira_host {
 using namespace mira;
 
+// The table is built on the stream of the commit that needs it (`st`): every kernel that reads it is queued behind
+// k_precompute on the same stream, so a lazily built table can never be read half-written (ctx->stream, where it used
+// to be built, is non-blocking and unordered with respect to a caller's stream).
 template <class CF>
-int build_table(mira_msm_ctx* ctx, int c, uint32_t n_cover, Table* out) {
+int build_table(mira_msm_ctx* ctx, int c, uint32_t n_cover, Table* out, cudaStream_t st) {
   int W = windows_for(c);
   void* d = nullptr;
   size_t bytes = (size_t)W * n_cover * 64;
   cudaError_t e = cudaMalloc(&d, bytes);
-  if (e != cudaSuccess)
+  if (e != cudaSuccess) {
+    cudaGetLastError();
     return fail(MIRA_ERR_CUDA, "cudaMalloc(%zu) for the fixed-base table failed: %s", bytes, cudaGetErrorString(e));
-  k_precompute<CF><<<(n_cover + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_bases, n_cover, c, W, d);
+  }
+  k_precompute<CF><<<(n_cover + 127) / 128, 128, 0, st>>>(ctx->d_bases, n_cover, c, W, d);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     cudaFree(d);
@@ -29,14 +34,23 @@ int build_table(mira_msm_ctx* ctx, int c, uint32_t n_cover, Table* out) {
   out->W = W;
   out->n_cover = n_cover;
   out->d = d;
+  out->bytes = bytes;
   return MIRA_OK;
 }
 
-// returns the table for window c covering at least n points (building it on first use)
+// Returns the table for window c covering at least n points, building it on first use.  The cache is bounded:
+//   * a table is only built if it fits beside TABLE_RESERVE bytes of free device memory (workspace of the commit
+//     itself); least-recently-used tables are evicted to make room (cudaFree synchronises the device, so no kernel
+//     still reads an evicted table);
+//   * if it cannot be built at all, the commit falls back to the cached table covering n whose window is closest to
+//     the one asked for (`*out` then has a different c: callers read the window from the table, not from the request).
+constexpr size_t TABLE_RESERVE = (size_t)6 << 30;
 template <class CF>
-int get_table(mira_msm_ctx* ctx, int c, size_t n, Table** out) {
+int get_table(mira_msm_ctx* ctx, int c, size_t n, cudaStream_t st, Table** out) {
+  ctx->table_clock++;
   for (auto& t : ctx->tables)
     if (t.c == c && t.n_cover >= n) {
+      t.last_use = ctx->table_clock;
       *out = &t;
       return MIRA_OK;
     }
@@ -53,11 +67,38 @@ int get_table(mira_msm_ctx* ctx, int c, size_t n, Table** out) {
       ++it;
     }
   }
-  Table t;
-  int rc = build_table<CF>(ctx, c, (uint32_t)cover, &t);
-  if (rc) return rc;
-  ctx->tables.push_back(t);
-  *out = &ctx->tables.back();
+  const size_t need = (size_t)windows_for(c) * cover * 64;
+  int rc = MIRA_ERR_CUDA;
+  for (;;) {
+    size_t free_b = 0, total_b = 0;
+    bool fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need + TABLE_RESERVE <= free_b;
+    if (!fits && !ctx->tables.empty()) {          // evict the least recently used table and look again
+      auto lru = ctx->tables.begin();
+      for (auto it = ctx->tables.begin(); it != ctx->tables.end(); ++it)
+        if (it->last_use < lru->last_use) lru = it;
+      // ... unless it is the only fallback that covers n and the new table would not fit even without it
+      if (lru->n_cover >= n && need + TABLE_RESERVE > free_b + lru->bytes) break;
+      cudaFree(lru->d);
+      ctx->tables.erase(lru);
+      continue;
+    }
+    Table t;
+    rc = build_table<CF>(ctx, c, (uint32_t)cover, &t, st);
+    if (rc == MIRA_OK) {
+      t.last_use = ctx->table_clock;
+      ctx->tables.push_back(t);
+      *out = &ctx->tables.back();
+      return MIRA_OK;
+    }
+    break;
+  }
+  // fallback: the cached table covering n with the closest window
+  Table* best = nullptr;
+  for (auto& t : ctx->tables)
+    if (t.n_cover >= n && (!best || std::abs(t.c - c) < std::abs(best->c - c))) best = &t;
+  if (!best) return rc != MIRA_OK ? rc : fail(MIRA_ERR_CUDA, "no device memory for a fixed-base table of %zu bytes (window %d, %zu points)", need, c, cover);
+  best->last_use = ctx->table_clock;
+  *out = best;
   return MIRA_OK;
 }
 
@@ -146,6 +187,18 @@ inline int affine_levels_for(const mira_msm_ctx* ctx) {
   return want < 0 ? 0 : (want > PA_MAX_LEVELS ? PA_MAX_LEVELS : want);
 }
 
+// Entries per accumulation thread: as long as possible (each chunk edge that falls inside a bucket's run costs one XYZZ
+// full add in k_combine, and a thread's first pair pays its load latency alone) while keeping the machine full: two
+// waves of 148 SMs x 512 resident threads below 32 M pairs, four above, never fewer than 32 pairs per thread
+// (measured sweep, 2^16..2^22 points: 2^19 2.07 -> 1.64 ms, 2^16 0.40 -> 0.30 ms against the former 4 waves / 16).
+inline int acc_chunk_len(size_t EA) {
+  static const unsigned waves_env = [] { const char* e = getenv("MIRA_ACC_WAVES"); return e ? (unsigned)atoi(e) : 0u; }();
+  static const int lmin = [] { const char* e = getenv("MIRA_ACC_LMIN"); return e ? atoi(e) : 32; }();
+  const unsigned waves = waves_env ? waves_env : (EA < ((size_t)32 << 20) ? 2u : 4u);
+  int L = (int)(EA / (148u * 512u * waves));
+  return L < lmin ? lmin : (L > 256 ? 256 : L);
+}
+
 struct MsmPlan {
   struct Prepared {                 // a decomposed and sorted slice, waiting in buffer set `bs` for its accumulation
     const uint32_t* skeys = nullptr;
@@ -169,7 +222,8 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
   int rc;
   int c = ctx->forced_window ? ctx->forced_window : (window ? window : choose_window(n));
   Table* tab = nullptr;
-  if ((rc = get_table<CF>(ctx, c, n, &tab))) return rc;
+  if ((rc = get_table<CF>(ctx, c, n, st, &tab))) return rc;
+  c = tab->c;                 // the cache may have handed out a neighbouring window (memory budget)
   const int W = tab->W;
   const size_t E = max_slice * (size_t)W * (size_t)n_sets;
   const uint32_t B = 1u << (c - 1);
@@ -185,6 +239,15 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
       return rc;
   }
   if ((rc = ctx->buckets.ensure(bucket_bytes))) return rc;
+  {
+    // the accumulation's scratch is sized here, once, from the largest slice: growing it between slices would
+    // cudaFree (a device-wide synchronisation) in the middle of the slice pipeline
+    const int L = acc_chunk_len(E);
+    const size_t n_chunks = (E + L - 1) / L, heavy_cap = n_chunks / HEAVY_CHUNKS + 2;
+    if ((rc = ctx->part_keys.ensure(n_chunks * 8)) || (rc = ctx->part_pts.ensure(n_chunks * 256)) ||
+        (rc = ctx->cursor.ensure((heavy_cap * 2 + 4) * 4)))
+      return rc;
+  }
   CU(cudaMemsetAsync(ctx->buckets.p, 0, bucket_bytes, st));
   plan->c = c; plan->W = W; plan->tab = tab; plan->B = B; plan->max_slice = max_slice; plan->n_sets = n_sets;
   plan->launches = 0; plan->entries = 0;
@@ -306,17 +369,9 @@ int msm_acc(mira_msm_ctx* ctx, MsmPlan* plan, bool add_mode, int bs, cudaStream_
   }
   // ---- accumulate
   {
-    // Entries per thread: as long as possible (each chunk edge that falls inside a bucket's run costs one XYZZ full
-    // add in k_combine, and a thread's first pair pays its load latency alone) while keeping the machine full: two
-    // waves of 148 SMs x 512 resident threads below 32 M pairs, four above, never fewer than 32 pairs per thread
-    // (measured sweep, 2^16..2^22 points: 2^19 2.07 -> 1.64 ms, 2^16 0.40 -> 0.30 ms against the former 4 waves / 16).
     // Sized from the upper bound n*W; grids cover that bound and surplus threads exit on the device-side pair count.
-    static const unsigned waves_env = [] { const char* e = getenv("MIRA_ACC_WAVES"); return e ? (unsigned)atoi(e) : 0u; }();
-    static const int lmin = [] { const char* e = getenv("MIRA_ACC_LMIN"); return e ? atoi(e) : 32; }();
     const size_t EA = acc_bound;
-    const unsigned waves = waves_env ? waves_env : (EA < ((size_t)32 << 20) ? 2u : 4u);
-    int L = (int)(EA / (148u * 512u * waves));
-    L = L < lmin ? lmin : (L > 256 ? 256 : L);
+    const int L = acc_chunk_len(EA);
     uint32_t n_chunks = (uint32_t)((EA + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
     if (acc_direct)
@@ -695,12 +750,17 @@ int combine_dev_impl(const void* d_partials, size_t n_ranks, size_t n_commits, s
   return MIRA_OK;
 }
 
-template <class CF>
-int prepare_impl(mira_msm_ctx* ctx, size_t n) {
-  int c = ctx->forced_window ? ctx->forced_window : choose_window(n);
+// prepare(n): the table the size-only heuristic picks.  prepare_for(scalars, n): the table the ADAPTIVE path will pick
+// for vectors that look like `scalars` (a sample decides; sparse witness columns want a much narrower window than
+// choose_window(n)), so that the first real commit of such a vector does not build a multi-gigabyte table inside its
+// timed region.
+template <class CF, class SF>
+int prepare_impl(mira_msm_ctx* ctx, size_t n, const void* like_scalars, int on_device) {
+  int rc, window = 0;
+  if (like_scalars && (rc = pick_window<SF>(ctx, like_scalars, n, on_device != 0, ctx->stream, &window))) return rc;
+  int c = ctx->forced_window ? ctx->forced_window : (window ? window : choose_window(n));
   Table* t = nullptr;
-  int rc = get_table<CF>(ctx, c, n, &t);
-  if (rc) return rc;
+  if ((rc = get_table<CF>(ctx, c, n, ctx->stream, &t))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   return MIRA_OK;
 }

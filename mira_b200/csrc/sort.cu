@@ -269,13 +269,14 @@ size_t radix_sort_temp_bytes(size_t max_pairs) {
 // between the a/b buffers; *sorted_in_b tells where the result ends up.  All launches go to `st`.
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
                      size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches) {
-  static bool attr_set[64] = {false};
+  static std::once_flag attr_once[64];       // the attribute is per device; contexts of several keys may race here
   int dev = 0;
   CU(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    CU(cudaFuncSetAttribute(k_radix_scatter<RS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<RS_THREADS>)));
-    attr_set[dev] = true;
-  }
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once[dev & 63], [&] {
+    attr_err = cudaFuncSetAttribute(k_radix_scatter<RS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<RS_THREADS>));
+  });
+  CU(attr_err);
   const uint32_t n_tiles = (uint32_t)((max_pairs + RS_TILE - 1) / RS_TILE);
   if (n_tiles == 0) {
     *sorted_in_b = 0;

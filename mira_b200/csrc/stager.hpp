@@ -85,9 +85,12 @@ struct Stager {
   cudaError_t init() {
     if (pool) return cudaSuccess;
     for (int i = 0; i < SLOTS; i++) {
-      cudaError_t e = cudaMallocHost(&slot[i], SLOT_BYTES);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming);
-      if (e != cudaSuccess) return e;
+      cudaError_t e = slot[i] ? cudaSuccess : cudaMallocHost(&slot[i], SLOT_BYTES);
+      if (e == cudaSuccess && !slot_free[i]) e = cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) {          // leave nothing half-made behind: the next commit starts from scratch
+        release();
+        return e;
+      }
     }
     unsigned hw = std::thread::hardware_concurrency();
     pool = new CopyPool(hw >= 16 ? 6 : (hw >= 8 ? 4 : 2));

@@ -1,0 +1,154 @@
+"""GPU parity at the sizes and window widths the headline metric is quoted on: the CUDA
+commit (through the C ABI) against the CPU oracle on identical bytes, bit for bit, at 2^20 and 2^22 points, at the
+window widths the 2^24 (c = 22) and 2^26 (c = 24) configurations use, on a lazily built table behind a caller's
+stream, and on Ethereum's public alt_bn128 vectors.  Run on the B200 box: pytest -m gpu."""
+import json
+import os
+
+import pytest
+
+import oracle_lib as O
+import pyref as R
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("curve,logn", [(R.BN254, 20), (R.GRUMPKIN, 20), (R.BN254, 22), (R.GRUMPKIN, 22)])
+def test_commit_2_20_and_2_22_vs_oracle(gpu, curve, logn):
+    """'every timed result compared bit-for-bit with the oracle at <= 2^20' and one oracle run above it.
+    Uniform scalars use the size heuristic's window (c = 19 / 20 here), witness-like ones the sampled window; both from
+    device memory and, for the uniform vector, through the host-buffer call with its H2D slices."""
+    from mira_b200 import CommitmentKey
+    n = 1 << logn
+    bases_dev = gpu.gen_bases_dev(curve, 0x4D495241, n)
+    bases = gpu.to_bytes(bases_dev)
+    ck = CommitmentKey(curve, bases_dev, on_device=True)
+    windows = {}
+    for dist in (0, 1):
+        sc = gpu.gen_scalars_dev(curve, 0x4D495242 + dist, n, dist)
+        host_sc = gpu.to_bytes(sc)
+        want = O.commit(curve, bases, host_sc)
+        assert ck.commit_device(sc.data_ptr(), n) == want, (curve, logn, dist)
+        windows[dist] = ck.stats()["window_bits"]
+        if dist == 0:
+            assert ck.commit(host_sc) == want
+            # a ragged prefix of the same key (prefix-of-key semantics, src/commitment.rs:80)
+            m = n - 12345
+            assert ck.commit_device(sc.data_ptr(), m) == O.commit(curve, bases[: 64 * m], host_sc[: 32 * m])
+    assert windows[0] >= 18 and windows[1] < windows[0]
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+@pytest.mark.parametrize("c", [22, 24])
+def test_headline_window_widths_vs_oracle(gpu, curve, c):
+    """c = 22 is what a 2^24-point commit runs with, c = 24 what 2^26 runs with (2^21 / 2^23 buckets, 12 / 11 windows):
+    the same kernels, launch shapes and reduction depths, on 2^17 + 1 points so that the oracle finishes in a second."""
+    from mira_b200 import CommitmentKey
+    n = (1 << 17) + 1
+    bases_dev = gpu.gen_bases_dev(curve, 2224, n)
+    bases = gpu.to_bytes(bases_dev)
+    ck = CommitmentKey(curve, bases_dev, on_device=True)
+    ck.set_window(c)
+    for dist in (0, 1):
+        sc = gpu.gen_scalars_dev(curve, 2225 + dist, n, dist)
+        host_sc = gpu.to_bytes(sc)
+        want = O.commit(curve, bases, host_sc)
+        assert ck.commit_device(sc.data_ptr(), n) == want
+        st = ck.stats()
+        assert st["window_bits"] == c and st["buckets"] == 1 << (c - 1)
+        assert ck.commit(host_sc) == want
+    # the largest window the ABI accepts
+    ck.set_window(26)
+    sc = gpu.gen_scalars_dev(curve, 2230, 4097, 0)
+    assert ck.commit_device(sc.data_ptr(), 4097) == O.commit(curve, bases[: 64 * 4097], gpu.to_bytes(sc))
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_lazy_table_is_built_on_the_callers_stream(gpu, curve):
+    """a fresh key, no prepare(), a non-default stream and >= 2^18 sparse scalars: the fixed-base table
+    is built lazily inside the commit and must be complete before the accumulation reads it.  Then the case that was
+    reachable after prepare(n): prepare builds the uniform-scalar table, the sampled window of a sparse vector needs
+    another one, built on first use on the caller's stream."""
+    from mira_b200 import CommitmentKey
+    n = (1 << 18) + 3
+    bases_dev = gpu.gen_bases_dev(curve, 4242, n)
+    bases = gpu.to_bytes(bases_dev)
+    s = torch.cuda.Stream()
+    sparse = gpu.gen_scalars_dev(curve, 4243, n, 1)
+    dense = gpu.gen_scalars_dev(curve, 4244, n, 0)
+    want_sparse = O.commit(curve, bases, gpu.to_bytes(sparse))
+    want_dense = O.commit(curve, bases, gpu.to_bytes(dense))
+    torch.cuda.synchronize()
+    ck = CommitmentKey(curve, bases_dev, on_device=True)            # fresh: no table yet
+    assert ck.commit_device(sparse.data_ptr(), n, s.cuda_stream) == want_sparse
+    ck2 = CommitmentKey(curve, bases_dev, on_device=True)
+    ck2.prepare(n)                                                   # the table uniform scalars use
+    c_uniform = None
+    assert ck2.commit_device(dense.data_ptr(), n, s.cuda_stream) == want_dense
+    c_uniform = ck2.stats()["window_bits"]
+    assert ck2.commit_device(sparse.data_ptr(), n, s.cuda_stream) == want_sparse     # builds the narrow table now
+    assert ck2.stats()["window_bits"] < c_uniform
+    # prepare(like=...) builds the table the adaptive path picks, so the commit itself launches no k_precompute
+    ck3 = CommitmentKey(curve, bases_dev, on_device=True)
+    ck3.prepare(n, like=sparse.data_ptr(), like_on_device=True)
+    assert ck3.commit_device(sparse.data_ptr(), n, s.cuda_stream) == want_sparse
+    assert ck3.stats()["window_bits"] == ck2.stats()["window_bits"]
+
+
+def test_null_stream_orders_producer_and_commit(gpu):
+    """NULL means the legacy default stream for every entry point that reads device scalars, as it
+    does for the witness kernels: fold_w(..., NULL) followed by commit_device(..., NULL) needs no synchronisation."""
+    from mira_b200 import CommitmentKey
+    from mira_b200 import witness as W
+    curve, field = R.BN254, R.FR
+    n = (1 << 19) + 7
+    bases_dev = gpu.gen_bases_dev(curve, 77, n)
+    ck = CommitmentKey(curve, bases_dev, on_device=True)
+    ck.prepare(n)
+    w1 = gpu.gen_scalars_dev(curve, 78, n, 0)
+    w2 = gpu.gen_scalars_dev(curve, 79, n, 0)
+    r = R.to_mont_bytes(R.gen_scalar(curve, 80, 0), R.scalar_mod(curve))
+    want_vec = O.fold_w(field, gpu.to_bytes(w1), gpu.to_bytes(w2), r)
+    want = O.commit(curve, gpu.to_bytes(bases_dev), want_vec)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        out = torch.zeros_like(w1)
+        W.fold_w(field, w1, w2, r, out=out)                      # default (NULL) stream, asynchronous
+        got = ck.commit_device(out.data_ptr(), n)                # default (NULL) stream: ordered behind the fold
+        assert got == want
+
+
+def test_eip196_vectors_on_the_gpu(gpu):
+    """Ethereum's alt_bn128 ecAdd / ecMul vectors (tests/golden/eip196_alt_bn128.json, an authority outside this
+    repository) through CommitmentKey::commit on the GPU: an MSM with unit scalars is ecAdd, an MSM of one term ecMul."""
+    from mira_b200 import CommitmentKey
+    with open(os.path.join(os.path.dirname(__file__), "golden", "eip196_alt_bn128.json")) as f:
+        v = json.load(f)
+
+    def pt(xy):
+        return R.point_to_bytes((int(xy[0], 16), int(xy[1], 16)), R.BN254)
+    one = R.to_mont_bytes(1, R.R_)
+    for c in v["ec_add"]:
+        ck = CommitmentKey(R.BN254, pt(c["a"]) + pt(c["b"]))
+        ck.check_on_curve()
+        assert ck.commit(one + one) == pt(c["sum"])
+    for c in v["ec_mul"]:
+        ck = CommitmentKey(R.BN254, pt(c["p"]))
+        assert ck.commit(R.to_mont_bytes(int(c["k"], 16), R.R_)) == pt(c["product"])
+    # the two chfast1 cases in one 3-term MSM, at every window width class (tiny, medium, headline)
+    ca, cm = v["ec_add"][1], v["ec_mul"][1]
+    ck = CommitmentKey(R.BN254, pt(cm["p"]) + pt(ca["a"]) + pt(ca["b"]))
+    want = R.point_to_bytes(R.add(tuple(int(t, 16) for t in cm["product"]), tuple(int(t, 16) for t in ca["sum"]), R.BN254), R.BN254)
+    for c in (0, 4, 13, 22):
+        ck.set_window(c)
+        assert ck.commit(R.to_mont_bytes(int(cm["k"], 16), R.R_) + one + one) == want

@@ -234,3 +234,53 @@ def test_golden_commit_vectors_freeze_the_oracle():
         assert O.commit(v["curve"], bases, sc).hex() == v["commit_hex"]
         if v["n"] <= 64:
             assert O.commit_naive(v["curve"], bases, sc).hex() == v["commit_hex"]
+
+
+# ---- external pin of the curve layer: Ethereum's alt_bn128 (= BN254 G1) precompile vectors, EIP-196 ----------------
+def _eip196():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "eip196_alt_bn128.json")) as f:
+        return json.load(f)
+
+
+def _pt(xy):
+    return R.point_to_bytes((int(xy[0], 16), int(xy[1], 16)), R.BN254)
+
+
+def test_eip196_vectors_are_self_consistent():
+    """The recorded vectors against an independent chord-and-tangent computation on Python integers (no oracle code):
+    guards the fixture itself against transcription errors."""
+    v = _eip196()
+    for c in v["ec_add"]:
+        a, b, s = (tuple(int(t, 16) for t in c[k]) for k in ("a", "b", "sum"))
+        assert R.is_on_curve(a, R.BN254) and R.is_on_curve(b, R.BN254) and R.add(a, b, R.BN254) == s
+    for c in v["ec_mul"]:
+        p, s = (tuple(int(t, 16) for t in c[k]) for k in ("p", "product"))
+        assert R.is_on_curve(p, R.BN254) and R.mul(int(c["k"], 16), p, R.BN254) == s
+
+
+def test_oracle_matches_eip196_ecadd_ecmul():
+    """oracle point_add / scalar_mul / commit (the restated best_multiexp + to_affine, i.e. what CommitmentKey::commit
+    returns, src/commitment.rs:78-87) reproduce the public alt_bn128 vectors: a pin of the oracle's G1 arithmetic,
+    Montgomery layout included, that does not come from this repository."""
+    v = _eip196()
+    one = R.to_mont_bytes(1, R.R_)
+    for c in v["ec_add"]:
+        a, b, s = _pt(c["a"]), _pt(c["b"]), _pt(c["sum"])
+        assert O.is_on_curve(R.BN254, a) and O.is_on_curve(R.BN254, b)
+        assert O.point_add(R.BN254, a, b) == s
+        assert O.commit(R.BN254, a + b, one + one) == s              # MSM with unit scalars = ecAdd
+        assert O.commit_naive(R.BN254, a + b, one + one) == s
+    for c in v["ec_mul"]:
+        p, s, k = _pt(c["p"]), _pt(c["product"]), R.to_mont_bytes(int(c["k"], 16), R.R_)
+        assert O.scalar_mul(R.BN254, p, k) == s
+        assert O.commit(R.BN254, p, k) == s                          # MSM of one term = ecMul
+    # both at once: k*P + 1*A + 1*B through the Pippenger path with padding points
+    c_add, c_mul = v["ec_add"][1], v["ec_mul"][1]
+    bases = _pt(c_mul["p"]) + _pt(c_add["a"]) + _pt(c_add["b"])
+    scal = R.to_mont_bytes(int(c_mul["k"], 16), R.R_) + one + one
+    want = O.point_add(R.BN254, _pt(c_mul["product"]), _pt(c_add["sum"]))
+    assert O.commit(R.BN254, bases, scal) == want
+    assert R.point_from_bytes(want, R.BN254) == R.add(tuple(int(t, 16) for t in c_mul["product"]),
+                                                       tuple(int(t, 16) for t in c_add["sum"]), R.BN254)

@@ -71,8 +71,7 @@ class GpuFoldStep:
             ck = CommitmentKey(curve, bases, device=device, on_device=True)
             ck.prepare(n_w)
             ck.prepare(rows)
-            del bases
-            st = {"ck": ck,
+            st = {"ck": ck, "bases": bases,
                   "fixed": [gen(10 + i, rows, 1) for i in range(s["meta"]["num_fixed"])],
                   "W1": gen(1, n_w, 0),            # accumulator (relaxed witness): dense
                   "E": gen(2, rows, 0),
@@ -131,7 +130,7 @@ class GpuFoldStep:
         out = []
         for s, st in zip(self.sh, self.state):
             out.append({k: ([gpu_util.to_bytes(x) for x in st[k]] if isinstance(st[k], list) else gpu_util.to_bytes(st[k]))
-                        for k in ("fixed", "W1", "E", "W2")} | {"ch": st["ch"], "r": st["r"]})
+                        for k in ("fixed", "W1", "E", "W2", "bases")} | {"ch": st["ch"], "r": st["r"]})
         return out
 
 
@@ -250,7 +249,7 @@ class CpuFoldStep:
             else:
                 d = inputs[ci]
             arr = lambda b: np.frombuffer(bytearray(b), dtype=np.uint8)
-            st = {"bases": arr(O.gen_bases(curve, SEED + ci, n_w)), "fixed": [arr(x) for x in d["fixed"]], "W1": arr(d["W1"]),
+            st = {"bases": arr(d["bases"]) if "bases" in d else arr(O.gen_bases(curve, SEED + ci, n_w)), "fixed": [arr(x) for x in d["fixed"]], "W1": arr(d["W1"]),
                   "E": arr(d["E"]), "W2": arr(d["W2"]), "ch": arr(d["ch"]), "r": arr(d["r"]),
                   "T": [np.zeros(rows * 32, dtype=np.uint8) for _ in s["progs"]],
                   "W_out": np.zeros(n_w * 32, dtype=np.uint8), "E_out": np.zeros(rows * 32, dtype=np.uint8)}
