@@ -51,6 +51,22 @@ const char *mira_last_error(void);
  * `bases` may be a host pointer (bases_on_device = 0) or a device pointer on `device` (= 1). */
 int mira_msm_ctx_create(int curve, const void *bases, size_t n_bases, int bases_on_device, int device,
                         mira_msm_ctx **out);
+/* The same key spread over several GPUs of ONE process -- what the reference's prover is (one process, rayon threads,
+ * Cargo.toml:36; `commit` is a plain method call, src/commitment.rs:78-87).  `bases` is a HOST pointer; device
+ * devices[g] keeps the contiguous point range g of n_devices balanced ranges (first n % n_devices ranges one point
+ * longer) and its own window tables (a device may be listed more than once; it then holds several ranges -- only
+ * useful to exercise the sharded path on a box with fewer GPUs).  mira_msm_commit on the returned context cuts the host scalar vector the same
+ * way (prefix semantics: range g commits v[lo_g .. min(hi_g, n))), drives every device from its own host thread (own
+ * PCIe link, own streams), moves the 128-byte XYZZ partial sums to devices[0] by peer copy and adds and normalises
+ * them there: the result is bit-identical to a single-device commit.  On such a context: mira_msm_ctx_len,
+ * _check_on_curve, _prepare, _prepare_for (host vectors), mira_msm_commit, mira_msm_get_stats (pairs and launches
+ * summed over the devices) and the mira_msm_set_* knobs (applied to every device) work as usual; entry points that
+ * take device-resident vectors (commit_device, commit_batch, partial*, scalars_device) return MIRA_ERR_INVALID /
+ * NULL -- a device vector lives on one GPU; row-sharded provers use one context per device (partial_batch_dev). */
+int mira_msm_ctx_create_sharded(int curve, const void *bases, size_t n_bases, const int *devices, size_t n_devices,
+                                mira_msm_ctx **out);
+/* number of devices a context spans (1 for mira_msm_ctx_create) */
+size_t mira_msm_ctx_num_devices(const mira_msm_ctx *ctx);
 void mira_msm_ctx_destroy(mira_msm_ctx *ctx);
 /* CommitmentKey::len (src/commitment.rs:44-46) */
 size_t mira_msm_ctx_len(const mira_msm_ctx *ctx);

@@ -25,14 +25,14 @@ MIRA_EVAL_LOOKUP_DOMAIN = 1
 
 # every symbol include/mira_b200.h declares (tests/test_capi_symbols.py checks the .so exports them all)
 SYMBOLS = [
-    "mira_last_error", "mira_msm_ctx_create", "mira_msm_ctx_destroy", "mira_msm_ctx_len",
+    "mira_last_error", "mira_msm_ctx_create", "mira_msm_ctx_create_sharded", "mira_msm_ctx_num_devices", "mira_msm_ctx_destroy", "mira_msm_ctx_len",
     "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_ctx_prepare_for", "mira_msm_commit", "mira_msm_commit_device", "mira_msm_commit_batch", "mira_msm_scalars_device",
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
     "mira_msm_set_window", "mira_msm_set_adaptive_window", "mira_msm_set_slice_min", "mira_msm_set_affine_levels", "mira_msm_set_pipeline", "mira_msm_partial_batch_dev", "mira_msm_combine_dev", "mira_host_register", "mira_host_unregister", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
     "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_lookup_m", "mira_lookup_h_g", "mira_fft", "mira_fft_std", "mira_test_eval_link_multi", "mira_eval_rows_multi",
 ]
-_VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_eval_program_destroy", "mira_msm_scalars_device")
+_VOID = ("mira_last_error", "mira_msm_ctx_destroy", "mira_msm_ctx_len", "mira_msm_ctx_num_devices", "mira_eval_program_destroy", "mira_msm_scalars_device")
 
 
 class EvalDomain(C.Structure):
@@ -78,6 +78,9 @@ def lib():
     vp, sz, i, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
     L.mira_last_error.restype = C.c_char_p
     L.mira_msm_ctx_create.argtypes = [i, vp, sz, i, i, C.POINTER(vp)]
+    L.mira_msm_ctx_create_sharded.argtypes = [i, vp, sz, C.POINTER(C.c_int), sz, C.POINTER(vp)]
+    L.mira_msm_ctx_num_devices.argtypes = [vp]
+    L.mira_msm_ctx_num_devices.restype = sz
     L.mira_msm_ctx_destroy.argtypes = [vp]
     L.mira_msm_ctx_destroy.restype = None
     L.mira_msm_ctx_len.argtypes = [vp]

@@ -80,6 +80,25 @@ class CommitmentKey:
         self._ctx = C.c_void_p()
         _check(L.mira_msm_ctx_create(curve, ptr, n, 1 if on_device else 0, device, C.byref(self._ctx)))
 
+    @classmethod
+    def sharded(cls, curve: int, bases, devices) -> "CommitmentKey":
+        """The key spread over several GPUs of this process (mira_msm_ctx_create_sharded): `bases` in HOST memory,
+        contiguous point ranges on `devices`; `commit(host_vector)` then runs on all of them and returns the same 64
+        bytes a single-device key returns.  Device-vector methods are not available on such a key."""
+        L = N.lib()
+        ptr, nbytes, keep = _as_ptr(bases)
+        self = cls.__new__(cls)
+        self.curve, self.device = curve, int(devices[0])
+        self._n = nbytes // POINT_BYTES
+        self._image, self._image_on_device = bases, False
+        self._ctx = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        _check(L.mira_msm_ctx_create_sharded(curve, ptr, self._n, devs, len(devices), C.byref(self._ctx)))
+        return self
+
+    def num_devices(self) -> int:
+        return int(N.lib().mira_msm_ctx_num_devices(self._ctx))
+
     # -- reference API -------------------------------------------------------------------------
     @staticmethod
     def default_value() -> bytes:

@@ -94,6 +94,12 @@ struct mira_msm_ctx {
   bool profiling = false;
   mira_msm_stats stats{};
   std::mutex mu;
+  // Single-process multi-GPU key (mira_msm_ctx_create_sharded): the parent holds no bases itself; shard g is an ordinary
+  // context over key indices [shard_lo[g], shard_lo[g + 1]) on its own device, and `gather` (on the parent's device)
+  // receives the shards' 128-byte XYZZ partial sums by peer copy.
+  std::vector<mira_msm_ctx*> shards;
+  std::vector<size_t> shard_lo;
+  mira_host::DevBuf gather;
 };
 
 namespace mira_host {
@@ -107,6 +113,7 @@ struct CurveOps {
   int (*combine)(const void* partials_host, size_t count, void* out_affine_host);
   int (*partial_batch_dev)(mira_msm_ctx*, const void* const* scalar_sets_dev, size_t count, size_t n, void* out_xyzz_dev, cudaStream_t st);
   int (*combine_dev)(const void* partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride, void* out_affine_host, cudaStream_t st);
+  int (*partial_to_peer)(mira_msm_ctx*, const void* scalars_host, size_t n, void* dst_dev, int dst_device, cudaStream_t st);
   int (*gen_scalars)(uint64_t seed, size_t first, size_t n, int dist, void* out_dev);
   int (*gen_bases)(uint64_t seed, size_t first, size_t n, void* out_dev);
   int (*test_point_op)(int op, const void* p_dev, const void* q_dev, size_t n, void* out_dev);

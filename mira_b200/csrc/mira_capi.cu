@@ -5,6 +5,9 @@
 // Per-curve device code lives in curve_bn254.cu / curve_grumpkin.cu (templates in pipeline.cuh).
 #include "ctx.hpp"
 
+#include <algorithm>
+#include <thread>
+
 namespace mira_host {
 
 static thread_local std::string g_err;
@@ -71,13 +74,81 @@ static cudaStream_t stream_for(mira_msm_ctx* ctx, int scalars_on_device, void* s
   return scalars_on_device ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : ctx->stream);
 }
 
+// ---- single-process multi-GPU key (mira_msm_ctx_create_sharded) ------------------------------------------------
+// CommitmentKey::commit uses the key prefix ck[..v.len()] (src/commitment.rs:80): shard g, which owns key indices
+// [lo, hi), commits v[lo .. min(hi, n)) -- possibly nothing.  One host thread per device drives that shard's ordinary
+// host-buffer pipeline (its own PCIe link, its own streams); the 128-byte XYZZ partial sums land in `gather` on the
+// parent's device by peer copy, and one kernel there adds them and normalises.  No collective library is needed inside
+// one process; across processes the same partials travel by an NCCL all_gather (mira_b200/sharding.py, bench.py).
+static int sharded_commit(mira_msm_ctx* ctx, const void* scalars, size_t n, void* out_affine) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const size_t G = ctx->shards.size();
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ctx->gather.ensure(G * 128))) return rc;
+  std::vector<int> rcs(G, MIRA_OK);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> workers;
+  workers.reserve(G);
+  for (size_t g = 0; g < G; g++) {
+    const size_t lo = ctx->shard_lo[g], hi = ctx->shard_lo[g + 1];
+    const size_t cnt = n > lo ? std::min(n, hi) - lo : 0;
+    workers.emplace_back([&, g, lo, cnt] {
+      mira_msm_ctx* sub = ctx->shards[g];
+      std::lock_guard<std::mutex> l2(sub->mu);
+      cudaError_t e = cudaSetDevice(sub->device);
+      if (e != cudaSuccess) {
+        rcs[g] = MIRA_ERR_CUDA;
+        errs[g] = cudaGetErrorString(e);
+        return;
+      }
+      rcs[g] = ops_for(sub->curve).partial_to_peer(sub, (const char*)scalars + lo * 32, cnt, (char*)ctx->gather.p + g * 128,
+                                                    ctx->device, sub->stream);
+      if (rcs[g]) errs[g] = g_err;       // the error text is thread-local: carry it to the calling thread
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (size_t g = 0; g < G; g++)
+    if (rcs[g]) return fail(rcs[g], "shard %zu (device %d): %s", g, ctx->shards[g]->device, errs[g].c_str());
+  CU(cudaSetDevice(ctx->device));
+  if ((rc = ops_for(ctx->curve).combine_dev(ctx->gather.p, G, 1, 128, out_affine, ctx->stream))) return rc;
+  // stats of the whole commit: pairs and launches summed over the shards, phase times of the slowest
+  mira_msm_stats agg{};
+  for (size_t g = 0; g < G; g++) {
+    const mira_msm_stats& s = ctx->shards[g]->stats;
+    if (g == 0) { agg.window_bits = s.window_bits; agg.windows = s.windows; agg.buckets = s.buckets; }
+    agg.entries += s.entries;
+    agg.kernel_launches += s.kernel_launches;
+    agg.ms_total = std::max(agg.ms_total, s.ms_total);
+  }
+  agg.kernel_launches += 1;
+  ctx->stats = agg;
+  return MIRA_OK;
+}
+
 static int dispatch_commit(mira_msm_ctx* ctx, const void* scalars, size_t n, int on_device, void* out, bool want_affine, void* stream) {
   if (!ctx || !out || (n && !scalars)) return fail(MIRA_ERR_INVALID, "null argument");
   if (n > ctx->n_bases)   // src/commitment.rs:79-86: checked before any arithmetic
     return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
+  if (!ctx->shards.empty()) {
+    if (on_device || !want_affine)
+      return fail(MIRA_ERR_INVALID, "a sharded (multi-device) context commits HOST scalar vectors to affine results only: device-resident "
+                                    "vectors live on one device; use one context per device and mira_msm_partial_batch_dev / mira_msm_combine_dev");
+    return sharded_commit(ctx, scalars, n, out);
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   return ops_for(ctx->curve).commit(ctx, scalars, n, on_device, out, want_affine, stream_for(ctx, on_device, stream));
+}
+
+// applies `fn` to every shard of a sharded context (first failure wins); false if the context is not sharded
+template <class Fn>
+static bool for_each_shard(mira_msm_ctx* ctx, int* rc, Fn fn) {
+  if (ctx->shards.empty()) return false;
+  *rc = MIRA_OK;
+  for (mira_msm_ctx* sub : ctx->shards)
+    if ((*rc = fn(sub)) != MIRA_OK) break;
+  return true;
 }
 
 }  // namespace mira_host
@@ -122,9 +193,64 @@ int mira_msm_ctx_create(int curve, const void* bases, size_t n_bases, int bases_
   return MIRA_OK;
 }
 
+int mira_msm_ctx_create_sharded(int curve, const void* bases, size_t n_bases, const int* devices, size_t n_devices, mira_msm_ctx** out) {
+  if (!out) return fail(MIRA_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!valid_curve(curve)) return fail(MIRA_ERR_INVALID, "unknown curve %d", curve);
+  if (!devices || n_devices == 0 || n_devices > 64) return fail(MIRA_ERR_INVALID, "a sharded context needs 1..64 devices");
+  if (n_bases && !bases) return fail(MIRA_ERR_INVALID, "bases is null");
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  for (size_t g = 0; g < n_devices; g++)
+    if (devices[g] < 0 || devices[g] >= count) return fail(MIRA_ERR_CUDA, "CUDA device %d not available (%d visible)", devices[g], count);
+  auto* ctx = new mira_msm_ctx();
+  ctx->curve = curve;
+  ctx->device = devices[0];
+  ctx->n_bases = n_bases;
+  // balanced contiguous ranges, the first n % G shards one point longer (mira_b200/sharding.py: shard_range)
+  const size_t q = n_bases / n_devices, r = n_bases % n_devices;
+  ctx->shard_lo.resize(n_devices + 1);
+  for (size_t g = 0; g <= n_devices; g++) ctx->shard_lo[g] = g * q + std::min(g, r);
+  int rc = MIRA_OK;
+  for (size_t g = 0; g < n_devices && rc == MIRA_OK; g++) {
+    mira_msm_ctx* sub = nullptr;
+    const size_t lo = ctx->shard_lo[g], cnt = ctx->shard_lo[g + 1] - lo;
+    rc = mira_msm_ctx_create(curve, (const char*)bases + lo * 64, cnt, 0, devices[g], &sub);
+    if (rc == MIRA_OK) {
+      ctx->shards.push_back(sub);
+      if (devices[g] != devices[0]) {       // direct peer copies of the partial sums; without peer access the driver stages them
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[g], devices[0]) == cudaSuccess && can) {
+          cudaSetDevice(devices[g]);
+          cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+          if (e != cudaSuccess) cudaGetLastError();       // already enabled, or not supported: not an error
+        }
+      }
+    }
+  }
+  if (rc == MIRA_OK) {
+    cudaError_t e = cudaSetDevice(devices[0]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) rc = fail(MIRA_ERR_CUDA, "sharded context creation failed: %s", cudaGetErrorString(e));
+  }
+  if (rc != MIRA_OK) {
+    std::string keep = g_err;
+    mira_msm_ctx_destroy(ctx);
+    g_err = keep;
+    return rc;
+  }
+  *out = ctx;
+  return MIRA_OK;
+}
+
+size_t mira_msm_ctx_num_devices(const mira_msm_ctx* ctx) { return ctx ? (ctx->shards.empty() ? 1 : ctx->shards.size()) : 0; }
+
 void mira_msm_ctx_destroy(mira_msm_ctx* ctx) {
   if (!ctx) return;
+  for (mira_msm_ctx* sub : ctx->shards) mira_msm_ctx_destroy(sub);
+  ctx->shards.clear();
   cudaSetDevice(ctx->device);
+  ctx->gather.release();
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& t : ctx->tables) cudaFree(t.d);
   for (DevBuf* b : {&ctx->scalars, &ctx->cursor, &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->result,
@@ -152,6 +278,8 @@ size_t mira_msm_ctx_len(const mira_msm_ctx* ctx) { return ctx ? ctx->n_bases : 0
 
 int mira_msm_ctx_check_on_curve(mira_msm_ctx* ctx) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  int frc;
+  if (for_each_shard(ctx, &frc, [](mira_msm_ctx* s) { return mira_msm_ctx_check_on_curve(s); })) return frc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   return ops_for(ctx->curve).check_on_curve(ctx);
@@ -161,6 +289,14 @@ int mira_msm_ctx_prepare(mira_msm_ctx* ctx, size_t n) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
   if (n > ctx->n_bases) return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
   if (n == 0) return MIRA_OK;
+  if (!ctx->shards.empty()) {           // every shard prepares for its share of a commit of length n
+    for (size_t g = 0; g < ctx->shards.size(); g++) {
+      const size_t lo = ctx->shard_lo[g], hi = ctx->shard_lo[g + 1];
+      int rc = n > lo ? mira_msm_ctx_prepare(ctx->shards[g], std::min(n, hi) - lo) : MIRA_OK;
+      if (rc) return rc;
+    }
+    return MIRA_OK;
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   return ops_for(ctx->curve).prepare(ctx, n, nullptr, 0);
@@ -170,6 +306,15 @@ int mira_msm_ctx_prepare_for(mira_msm_ctx* ctx, const void* scalars, size_t n, i
   if (!ctx || (n && !scalars)) return fail(MIRA_ERR_INVALID, "null argument");
   if (n > ctx->n_bases) return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
   if (n == 0) return MIRA_OK;
+  if (!ctx->shards.empty()) {
+    if (scalars_on_device) return fail(MIRA_ERR_INVALID, "a sharded context takes host vectors");
+    for (size_t g = 0; g < ctx->shards.size(); g++) {
+      const size_t lo = ctx->shard_lo[g], hi = ctx->shard_lo[g + 1];
+      int rc = n > lo ? mira_msm_ctx_prepare_for(ctx->shards[g], (const char*)scalars + lo * 32, std::min(n, hi) - lo, 0) : MIRA_OK;
+      if (rc) return rc;
+    }
+    return MIRA_OK;
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   return ops_for(ctx->curve).prepare(ctx, n, scalars, scalars_on_device);
@@ -192,6 +337,7 @@ int mira_msm_commit_batch(mira_msm_ctx* ctx, const void* const* scalars_dev, siz
     return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
   for (size_t k = 0; k < count; k++)
     if (n && !scalars_dev[k]) return fail(MIRA_ERR_INVALID, "vector %zu is null", k);
+  if (!ctx->shards.empty()) return fail(MIRA_ERR_INVALID, "device-resident vectors live on one device: not available on a sharded context");
   if (!count) return MIRA_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
@@ -212,6 +358,7 @@ int mira_msm_partial_batch_dev(mira_msm_ctx* ctx, const void* const* scalars_dev
     return fail(MIRA_ERR_TOO_LONG_INPUT, "Can't commit too long input: input len: %zu, but limit is %zu", n, ctx->n_bases);
   for (size_t k = 0; k < count; k++)
     if (n && !scalars_dev[k]) return fail(MIRA_ERR_INVALID, "vector %zu is null", k);
+  if (!ctx->shards.empty()) return fail(MIRA_ERR_INVALID, "device-resident vectors live on one device: not available on a sharded context");
   if (!count) return MIRA_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
@@ -236,12 +383,14 @@ int mira_msm_get_stats(const mira_msm_ctx* ctx, mira_msm_stats* out) {
 }
 int mira_msm_set_profiling(mira_msm_ctx* ctx, int enabled) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_profiling(sub, enabled); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->profiling = enabled != 0;
   return MIRA_OK;
 }
 int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_window(sub, window_bits); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (window_bits != 0 && (window_bits < 2 || window_bits > 26)) return fail(MIRA_ERR_INVALID, "window must be 0 or in [2, 26]");
   ctx->forced_window = window_bits;
@@ -251,7 +400,7 @@ int mira_msm_set_window(mira_msm_ctx* ctx, int window_bits) {
 const void* mira_msm_scalars_device(const mira_msm_ctx* ctx, size_t* n_out) {
   if (!ctx) return nullptr;
   std::lock_guard<std::mutex> lk(const_cast<mira_msm_ctx*>(ctx)->mu);
-  if (n_out) *n_out = ctx->scalars_valid;
+  if (n_out) *n_out = ctx->scalars_valid;      // 0 on a sharded context: the device copies are spread over the shards' devices
   return ctx->scalars_valid ? ctx->scalars.p : nullptr;
 }
 
@@ -274,6 +423,7 @@ int mira_host_unregister(void* host_ptr) {
 
 int mira_msm_set_adaptive_window(mira_msm_ctx* ctx, int enabled) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_adaptive_window(sub, enabled); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->adaptive_window = enabled != 0;
   return MIRA_OK;
@@ -281,6 +431,7 @@ int mira_msm_set_adaptive_window(mira_msm_ctx* ctx, int enabled) {
 
 int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_slice_min(sub, min_scalars_per_slice); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->slice_min = min_scalars_per_slice ? min_scalars_per_slice : ~(size_t)0;   // 0 = never slice
   return MIRA_OK;
@@ -288,6 +439,7 @@ int mira_msm_set_slice_min(mira_msm_ctx* ctx, size_t min_scalars_per_slice) {
 
 int mira_msm_set_pipeline(mira_msm_ctx* ctx, int slices, size_t min_scalars_per_slice) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_pipeline(sub, slices, min_scalars_per_slice); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (slices < 0 || slices > 16) return fail(MIRA_ERR_INVALID, "pipeline slices %d out of range [0, 16]", slices);
   ctx->pipe_slices = slices ? slices : -1;
@@ -297,6 +449,7 @@ int mira_msm_set_pipeline(mira_msm_ctx* ctx, int slices, size_t min_scalars_per_
 
 int mira_msm_set_affine_levels(mira_msm_ctx* ctx, int levels) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
+  { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_affine_levels(sub, levels); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (levels < 0 || levels > 6) return fail(MIRA_ERR_INVALID, "affine levels %d out of range [0, 6]", levels);
   ctx->affine_levels = levels;

@@ -754,6 +754,20 @@ int combine_dev_impl(const void* d_partials, size_t n_ranks, size_t n_commits, s
 // for vectors that look like `scalars` (a sample decides; sparse witness columns want a much narrower window than
 // choose_window(n)), so that the first real commit of such a vector does not build a multi-gigabyte table inside its
 // timed region.
+// One shard of a single-process multi-GPU commit (mira_msm_ctx_create_sharded): this device's slice of the HOST scalar
+// vector through the ordinary host-buffer pipeline, then the 128-byte XYZZ partial sum straight from this device's
+// memory into the gather buffer on the combining device (peer copy: NVLink when peer access is enabled, staged by the
+// driver otherwise).  Returns when the partial has landed.
+template <class CF, class SF>
+int partial_to_peer_impl(mira_msm_ctx* ctx, const void* h_scalars, size_t n, void* d_dst, int dst_device, cudaStream_t st) {
+  int rc;
+  if ((rc = msm_host<CF, SF>(ctx, h_scalars, n, st))) return rc;
+  if (dst_device == ctx->device) CU(cudaMemcpyAsync(d_dst, ctx->result.p, 128, cudaMemcpyDeviceToDevice, st));
+  else CU(cudaMemcpyPeerAsync(d_dst, dst_device, ctx->result.p, ctx->device, 128, st));
+  CU(cudaStreamSynchronize(st));
+  return MIRA_OK;
+}
+
 template <class CF, class SF>
 int prepare_impl(mira_msm_ctx* ctx, size_t n, const void* like_scalars, int on_device) {
   int rc, window = 0;

@@ -152,3 +152,35 @@ def test_eip196_vectors_on_the_gpu(gpu):
     for c in (0, 4, 13, 22):
         ck.set_window(c)
         assert ck.commit(R.to_mont_bytes(int(cm["k"], 16), R.R_) + one + one) == want
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_single_process_sharded_key_equals_single_device(gpu, curve):
+    """mira_msm_ctx_create_sharded: one process, the key cut into point ranges over a device list,
+    `commit` on it returns the bytes a single-device key returns (and the oracle's) for full, prefix, ragged, tiny and
+    empty vectors.  With one GPU the list names it several times (several ranges on one device: same code path, same
+    threads); with more, one range per GPU."""
+    from mira_b200 import CommitmentKey, TooLongInput
+    n = (1 << 18) + 11
+    bases = gpu.to_bytes(gpu.gen_bases_dev(curve, 9001, n))
+    ndev = torch.cuda.device_count()
+    lists = [[0], [0, 0, 0]] if ndev < 2 else [list(range(ndev)), [0, 1, 0]]
+    single = CommitmentKey(curve, bases)
+    for devices in lists:
+        ck = CommitmentKey.sharded(curve, bases, devices)
+        assert ck.len() == n and ck.num_devices() == len(devices)
+        ck.check_on_curve()
+        for dist, m in ((0, n), (1, n), (0, n - 70001), (0, n // len(devices) + 5), (0, 3), (0, 1), (0, 0)):
+            sc = O.gen_scalars(curve, 9002 + dist, m, dist)
+            got = ck.commit(sc)
+            assert got == single.commit(sc), (devices, dist, m)
+            if m in (n, 3, 0):
+                assert got == O.commit(curve, bases[: 64 * m], sc)
+        assert ck.stats()["entries"] == 0                      # the empty commit
+        ck.commit(O.gen_scalars(curve, 9010, n, 0))
+        assert ck.stats()["entries"] >= 10 * n                 # pairs summed over the shards (each picks its own window)
+        with pytest.raises(TooLongInput):
+            ck.commit(bytes(32 * (n + 1)))
+        with pytest.raises(ValueError):
+            ck.commit_device(0x1000, 1)                        # a device vector lives on ONE device: not on a sharded key
+        ck.close()
