@@ -134,6 +134,16 @@ int mira_msm_partial_batch_dev(mira_msm_ctx *ctx, const void *const *scalars_dev
 int mira_msm_combine_dev(int curve, const void *partials_dev, size_t n_ranks, size_t n_commits, size_t rank_stride,
                          int device, void *out_affine, void *stream);
 
+/* Plain device memory, for callers that have no CUDA runtime binding of their own (the Rust shim of INTEGRATION.md
+ * keeps fixed columns, witnesses and cross terms in HBM with these; Python callers use torch tensors instead).
+ * upload is asynchronous on `stream` (NULL = the legacy default stream, like every witness-side call); download
+ * returns when the bytes are in host memory; sync waits for `stream`. */
+int mira_dev_alloc(int device, size_t bytes, void **out_dev);
+int mira_dev_free(int device, void *dev_ptr);
+int mira_dev_upload(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int mira_dev_download(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int mira_dev_sync(int device, void *stream);
+
 /* Page-lock a host buffer the caller will commit from repeatedly (a witness column arena, the `Vec<C::Scalar>` a
  * prover re-uses every step).  mira_msm_commit works with any host memory, but only page-locked memory lets the
  * H2D copies of its slices run asynchronously at PCIe speed behind the accumulation of the previous slice; with

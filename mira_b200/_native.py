@@ -28,7 +28,7 @@ SYMBOLS = [
     "mira_last_error", "mira_msm_ctx_create", "mira_msm_ctx_create_sharded", "mira_msm_ctx_num_devices", "mira_msm_ctx_destroy", "mira_msm_ctx_len",
     "mira_msm_ctx_check_on_curve", "mira_msm_ctx_prepare", "mira_msm_ctx_prepare_for", "mira_msm_commit", "mira_msm_commit_device", "mira_msm_commit_batch", "mira_msm_scalars_device",
     "mira_msm_partial", "mira_msm_combine", "mira_msm_get_stats", "mira_msm_set_profiling",
-    "mira_msm_set_window", "mira_msm_set_adaptive_window", "mira_msm_set_slice_min", "mira_msm_set_affine_levels", "mira_msm_set_pipeline", "mira_msm_partial_batch_dev", "mira_msm_combine_dev", "mira_host_register", "mira_host_unregister", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
+    "mira_msm_set_window", "mira_msm_set_adaptive_window", "mira_msm_set_slice_min", "mira_msm_set_affine_levels", "mira_msm_set_pipeline", "mira_msm_partial_batch_dev", "mira_msm_combine_dev", "mira_dev_alloc", "mira_dev_free", "mira_dev_upload", "mira_dev_download", "mira_dev_sync", "mira_host_register", "mira_host_unregister", "mira_gen_scalars", "mira_gen_bases", "mira_test_field_op", "mira_test_point_op",
     "mira_fold_w", "mira_fold_e", "mira_concat_pad", "mira_eval_program_create", "mira_eval_program_destroy",
     "mira_eval_rows", "mira_eval_rows_range", "mira_eval_program_stats", "mira_lookup_m", "mira_lookup_h_g", "mira_fft", "mira_fft_std", "mira_test_eval_link_multi", "mira_eval_rows_multi",
 ]
@@ -104,6 +104,11 @@ def lib():
     L.mira_msm_partial_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp]
     L.mira_msm_combine_dev.argtypes = [i, vp, sz, sz, sz, i, vp, vp]
     L.mira_msm_set_adaptive_window.argtypes = [vp, i]
+    L.mira_dev_alloc.argtypes = [i, sz, C.POINTER(vp)]
+    L.mira_dev_free.argtypes = [i, vp]
+    L.mira_dev_upload.argtypes = [i, vp, vp, sz, vp]
+    L.mira_dev_download.argtypes = [i, vp, vp, sz, vp]
+    L.mira_dev_sync.argtypes = [i, vp]
     L.mira_host_register.argtypes = [vp, sz]
     L.mira_host_unregister.argtypes = [vp]
     L.mira_gen_scalars.argtypes = [i, u64, sz, sz, i, i, vp]

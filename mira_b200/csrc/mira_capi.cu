@@ -404,6 +404,40 @@ const void* mira_msm_scalars_device(const mira_msm_ctx* ctx, size_t* n_out) {
   return ctx->scalars_valid ? ctx->scalars.p : nullptr;
 }
 
+// ---- plain device memory for callers without a CUDA runtime binding of their own (the Rust shim)
+int mira_dev_alloc(int device, size_t bytes, void** out_dev) {
+  if (!out_dev) return fail(MIRA_ERR_INVALID, "null argument");
+  *out_dev = nullptr;
+  CU(cudaSetDevice(device));
+  cudaError_t e = cudaMalloc(out_dev, bytes ? bytes : 1);
+  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return MIRA_OK;
+}
+int mira_dev_free(int device, void* dev_ptr) {
+  if (!dev_ptr) return MIRA_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaFree(dev_ptr));
+  return MIRA_OK;
+}
+int mira_dev_upload(int device, void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+  if (bytes && (!dst_dev || !src_host)) return fail(MIRA_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return MIRA_OK;
+}
+int mira_dev_download(int device, void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+  if (bytes && (!dst_host || !src_dev)) return fail(MIRA_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return MIRA_OK;
+}
+int mira_dev_sync(int device, void* stream) {
+  CU(cudaSetDevice(device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return MIRA_OK;
+}
+
 int mira_host_register(void* host_ptr, size_t bytes) {
   if (!host_ptr || !bytes) return fail(MIRA_ERR_INVALID, "null argument");
   cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);

@@ -268,6 +268,17 @@ def main_gate_expr(T: int, col0: int, num_selectors: int, num_fixed_total: int, 
     return acc
 
 
+def relaxed_circuit(T: int, n_gates: int, modulus: int):
+    """Everything `is_sat_relaxed` (src/plonk/mod.rs:495-560) and `commit_cross_terms` need for a circuit shaped like
+    the reference's IVC circuits: the compressed gate expression, its homogeneous form over ONE instance (challenges
+    followed by u), the GraphEvaluator of that form, the cross-term programs and the column bookkeeping."""
+    progs, meta = cross_term_programs(T, n_gates, modulus)
+    hom = meta["hom"]
+    meta = dict(meta)
+    meta["hom_program"] = GraphEvaluator.new(hom, modulus)     # GraphEvaluator::new(custom_gates_lookup_compressed.homogeneous())
+    return progs, meta
+
+
 def cross_term_programs(T: int, n_gates: int, modulus: int):
     """Programs shaped like the reference's IVC circuits: `n_gates` MainGate<T> instances
     (1 for the secondary circuit, 2 for the primary), compressed with a challenge when n_gates > 1
@@ -293,5 +304,7 @@ def cross_term_programs(T: int, n_gates: int, modulus: int):
     coeffs = grouped(hom, is_folded, lambda idx: idx + num_advice, lambda ci: ci + per_instance)
     progs = [GraphEvaluator.new(c if c is not None else Constant(0), modulus) for c in coeffs[1:]]
     meta = {"num_selectors": num_selectors, "num_fixed": num_fixed, "num_advice": num_advice, "num_lookup": 0,
-            "num_challenges": 2 * per_instance, "degree": len(coeffs) - 1, "exprs": coeffs[1:]}
+            "num_challenges": 2 * per_instance, "degree": len(coeffs) - 1, "exprs": coeffs[1:],
+            "gate": expr, "hom": hom, "per_instance_challenges": per_instance, "fixed_per_gate": fixed_per,
+            "advice_per_gate": adv_per, "T": T, "n_gates": n_gates}
     return progs, meta

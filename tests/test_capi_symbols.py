@@ -55,7 +55,7 @@ def test_product_never_imports_the_oracle():
 
 
 def test_rust_bindings_are_current_and_complete():
-    """bindings/mira_b200_sys.rs (the `extern "C"` block of the Rust -sys crate) is generated from the
+    """integration/crates/mira-b200-sys/src/lib.rs (the `extern "C"` block of the Rust -sys crate) is generated from the
     header: the committed file must be what the generator emits now, and must declare exactly the exported symbols."""
     import sys
     from mira_b200 import _native as N

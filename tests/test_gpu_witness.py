@@ -453,3 +453,64 @@ def test_binding_cache_refreshes_challenges_and_notices_new_columns(W):
     gd2 = gpu_domain(W, d2)
     assert [host(g) for g in W.evaluate_rows_multi(gp, gd2)] == [O.eval_rows(FR, p, d2.as_bytes()) for p in packed]
     assert host(gp[0].evaluate_rows(gd)) == O.eval_rows(FR, packed[0], d1.as_bytes())
+
+
+# ---- is_sat_relaxed (src/plonk/mod.rs:495-560) on a folded instance, everything on the GPU
+@pytest.mark.parametrize("T,n_gates", [(5, 1), (5, 2)])
+def test_is_sat_relaxed_on_the_folded_instance(W, T, n_gates):
+    """The check `IVC::verify` runs on the accumulator (src/ivc/incrementally_verifiable_computation.rs:617-680) and the
+    reference's folding tests rely on (src/nifs/vanilla/tests.rs:137-244), at k = 11 through the C ABI:
+      commit_cross_terms   T_k = mira_eval_rows_multi over (W1, W2), C_Tk = mira_msm_commit_batch
+      fold                 W' = W1 + r W2, E' = E1 + sum r^k T_k        (mira_fold_w / mira_fold_e)
+      is_sat_relaxed       the un-grouped HOMOGENEOUS gate program over W' with challenges c' | u' (mira_eval_rows)
+                           == E' row by row;  commit(W') == C_W1 + r C_W2;  commit(E') == C_E1 + sum r^k C_Tk
+    with every device result also compared with the oracle's bytes."""
+    from mira_b200 import BN254_G1, CommitmentKey
+    from witness_util import RelaxedFold
+    f = RelaxedFold(M, 11, T, n_gates, seed=2000 + n_gates)
+    b, rows, meta = f.bytes(), f.rows, f.meta
+    n_w = meta["num_advice"] * rows
+    fixed = [dev(c) for c in b["fixed"]]
+    w1, w2, e1 = dev(b["w1"]), dev(b["w2"]), dev(b["e1"])
+    bases = O.gen_bases(R.BN254, 4711, n_w)
+    ck = CommitmentKey(BN254_G1, bases)
+    mk = lambda p: W.GraphEvaluator(FR, p["code"], p["constants"], p["rotations"], p["num_intermediates"])
+    # commit_cross_terms
+    dom12 = W.PlonkEvalDomain(meta["num_advice"], 0, b["challenges"], [], fixed, [w1], [w2])
+    progs = [mk(pack_program(p)) for p in f.progs]
+    cross = W.evaluate_rows_multi(progs, dom12)
+    want_cross = [O.eval_rows(FR, pack_program(p), f.domain_bytes(b["w1"], b["w2"], b["challenges"])) for p in f.progs]
+    assert [host(t) for t in cross] == want_cross
+    assert host(cross[-1]) == bytes(32 * rows)                       # T_d vanishes: the incoming instance is satisfied
+    c_t = ck.commit_batch_device([t.data_ptr() for t in cross], rows)
+    assert c_t[-1] == bytes(64)                                      # commitment to the zero vector is the identity
+    c_w1, c_w2, c_e1 = ck.commit(b["w1"]), ck.commit(b["w2"]), ck.commit(b["e1"])
+    # fold
+    w_f = W.fold_w(FR, w1, w2, b["r"])
+    e_f = W.fold_e(FR, e1, cross, b["r"])
+    assert host(w_f) == O.fold_w(FR, b["w1"], b["w2"], b["r"])
+    assert host(e_f) == O.fold_e(FR, b["e1"], want_cross, b["r"])
+    w_int, u, c = f.folded()
+    # is_sat_relaxed, evaluation half: hom(W'; c', u') == E' on every row
+    hom = mk(pack_program(meta["hom_program"]))
+    dom_f = W.PlonkEvalDomain(meta["num_advice"], 0, mont(c + [u], M), [], fixed, [w_f], [])
+    got = hom.evaluate_rows(dom_f)
+    torch.cuda.synchronize()
+    assert bool((got == e_f).all().item())                          # mismatch_count == 0
+    assert host(got) == O.eval_rows(FR, pack_program(meta["hom_program"]), f.domain_bytes(host(w_f), None, mont(c + [u], M)))
+    # ... and it does detect a violated row: perturb one cell of W'
+    bad = w_f.clone()
+    bad[32 * (3 * rows + 17)] ^= 1
+    got_bad = hom.evaluate_rows(W.PlonkEvalDomain(meta["num_advice"], 0, mont(c + [u], M), [], fixed, [bad], []))
+    diff = (got_bad.view(rows, 32) != e_f.view(rows, 32)).any(dim=1)
+    assert int(diff.sum().item()) == 1 and bool(diff[17].item())
+    # is_sat_relaxed, commitment half
+    want_cw = O.point_add(R.BN254, c_w1, O.scalar_mul(R.BN254, c_w2, b["r"]))
+    assert ck.commit_device(w_f.data_ptr(), n_w) == want_cw == O.commit(R.BN254, bases, host(w_f))
+    want_ce, rk = c_e1, 1
+    for ct in c_t:
+        rk = rk * f.r % M
+        want_ce = O.point_add(R.BN254, want_ce, O.scalar_mul(R.BN254, ct, R.to_mont_bytes(rk, M)))
+    assert ck.commit_device(e_f.data_ptr(), rows) == want_ce == O.commit(R.BN254, bases[: 64 * rows], host(e_f))
+    for p in progs + [hom]:
+        p.close()

@@ -285,3 +285,38 @@ def test_lookup_eval_domain_uses_separate_advice_columns():
     with pytest.raises(O.EvalError) as ex:
         O.eval_rows(FR, pack_program(G.GraphEvaluator.new(G.Polynomial(3 + 2), M)), dom)
     assert ex.value.rc == -13        # RowIndexOutOfBoundary
+
+
+@pytest.mark.parametrize("T,n_gates", [(5, 1), (5, 2)])
+def test_is_sat_relaxed_holds_on_the_folded_instance(T, n_gates):
+    """`is_sat_relaxed` (src/plonk/mod.rs:495-560) on the CPU: fold a satisfied incoming instance into a relaxed
+    accumulator through the oracle's evaluator, fold and commit; the homogeneous gate program evaluated on the folded
+    witness equals the folded error vector row by row, and re-committing W and E gives the homomorphically folded
+    commitments.  The same construction runs on the GPU in tests/test_gpu_witness.py."""
+    from witness_util import RelaxedFold
+    f = RelaxedFold(M, 6, T, n_gates, seed=1000 + n_gates)
+    assert all(v == 0 for v in f.incoming_gate_values())                 # the incoming instance is satisfied
+    b = f.bytes()
+    rows, meta = f.rows, f.meta
+    cross = [O.eval_rows(FR, pack_program(p), f.domain_bytes(b["w1"], b["w2"], b["challenges"])) for p in f.progs]
+    assert unmont(cross[-1], M) == [0] * rows                            # T_d = the gate on the incoming instance alone
+    w_f = O.fold_w(FR, b["w1"], b["w2"], b["r"])
+    e_f = O.fold_e(FR, b["e1"], cross, b["r"])
+    w_int, u, c = f.folded()
+    assert unmont(w_f, M) == w_int
+    # evaluation check of is_sat_relaxed: hom(W'; c', u') == E' for every row (oracle evaluator, then Python integers)
+    hom = pack_program(meta["hom_program"])
+    got = O.eval_rows(FR, hom, f.domain_bytes(w_f, None, mont(c + [u], M)))
+    assert got == e_f
+    assert unmont(e_f, M) == f.hom_on(w_int, c, u)
+    # commitment checks of is_sat_relaxed: commit(W') == C_W1 + r C_W2, commit(E') == C_E1 + sum r^k C_Tk
+    n_w = meta["num_advice"] * rows
+    bases = O.gen_bases(R.BN254, 31337, n_w)
+    cw = O.point_add(R.BN254, O.commit(R.BN254, bases, b["w1"]), O.scalar_mul(R.BN254, O.commit(R.BN254, bases, b["w2"]), b["r"]))
+    assert O.commit(R.BN254, bases, w_f) == cw
+    ce = O.commit(R.BN254, bases[: 64 * rows], b["e1"])
+    rk = 1
+    for t in cross:
+        rk = rk * f.r % M
+        ce = O.point_add(R.BN254, ce, O.scalar_mul(R.BN254, O.commit(R.BN254, bases[: 64 * rows], t), R.to_mont_bytes(rk, M)))
+    assert O.commit(R.BN254, bases[: 64 * rows], e_f) == ce

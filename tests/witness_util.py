@@ -101,3 +101,87 @@ def random_expr(rng, m, n_columns, n_challenges, depth, rotations=(0,)):
     if k < 0.6: return a - b
     if k < 0.65: return a * a
     return a * b
+
+
+class RelaxedFold:
+    """One folding step of a relaxed PLONK instance, built with plain Python integers, for `is_sat_relaxed`-shaped
+    tests (src/plonk/mod.rs:495-560; src/nifs/vanilla/mod.rs:220-251):
+
+      * incoming instance (W2, u2 = 1, E2 = 0): every MainGate row is SATISFIED -- the `out` cell of each gate is solved
+        from the gate equation (it is linear in `out`), the other cells and the fixed columns are random;
+      * accumulator (W1, u1, E1): random W1, random u1 and challenges, and E1 := hom(W1; c1, u1) row by row, i.e. a
+        relaxed instance that satisfies its relation by construction;
+      * challenge vector handed to the cross-term programs: c1 | u1 | c2 | 1 (src/nifs/vanilla/mod.rs:91).
+
+    All vectors are exposed as Montgomery byte strings in the reference's layouts (W column-major)."""
+
+    def __init__(self, m: int, log_rows: int, T: int, n_gates: int, seed: int):
+        rng = random.Random(seed)
+        self.m = m
+        self.rows = rows = 1 << log_rows
+        self.progs, self.meta = G.relaxed_circuit(T, n_gates, m)
+        meta = self.meta
+        nf, na, nch = meta["num_fixed"], meta["num_advice"], meta["per_instance_challenges"] - 1
+        fpg, apg = meta["fixed_per_gate"], meta["advice_per_gate"]
+
+        def sparse():
+            x = rng.random()
+            if x < 0.4: return 0
+            if x < 0.6: return 1
+            if x < 0.8: return rng.randrange(1 << 32)
+            return rng.randrange(m)
+        self.fixed = [[sparse() for _ in range(rows)] for _ in range(nf)]
+        for g in range(n_gates):                      # q_o must be invertible to solve for `out`
+            col = self.fixed[g * fpg + 3 * T + 1]
+            for r in range(rows):
+                if col[r] == 0:
+                    col[r] = 1 + rng.randrange(m - 1)
+        self.c1 = [rng.randrange(m) for _ in range(nch)]
+        self.c2 = [rng.randrange(m) for _ in range(nch)]
+        self.u1 = rng.randrange(m)
+        self.w1 = [rng.randrange(m) for _ in range(na * rows)]
+        self.w2 = [sparse() for _ in range(na * rows)]
+        # satisfy every gate of the incoming instance: gate_g(out = 0) + q_o * out = 0
+        gates = [G.main_gate_expr(T, g * apg, 0, nf, g * fpg) for g in range(n_gates)]
+        for g, ge in enumerate(gates):
+            out_col = g * apg + T + 1
+            for r in range(rows):
+                self.w2[out_col * rows + r] = 0
+                rest = G.eval_expr(ge, m, self._col(self.w2), [], r, rows)
+                q_o = self.fixed[g * fpg + 3 * T + 1][r]
+                self.w2[out_col * rows + r] = (-rest * pow(q_o, -1, m)) % m
+        # E1 := hom(W1; c1, u1)
+        self.e1 = [G.eval_expr(meta["hom"], m, self._col(self.w1), self.c1 + [self.u1], r, rows) for r in range(rows)]
+        self.r = rng.randrange(m)
+
+    def _col(self, w):
+        nf, rows = self.meta["num_fixed"], self.rows
+        return lambda index, row: self.fixed[index][row] if index < nf else w[(index - nf) * rows + row]
+
+    # what the reference computes on the CPU, with Python integers (independent of oracle/ and of the GPU)
+    def incoming_gate_values(self):
+        return [G.eval_expr(self.meta["gate"], self.m, self._col(self.w2), self.c2, r, self.rows) for r in range(self.rows)]
+
+    def folded(self):
+        m, r = self.m, self.r
+        w = [(a + r * b) % m for a, b in zip(self.w1, self.w2)]
+        u = (self.u1 + r) % m
+        c = [(a + r * b) % m for a, b in zip(self.c1, self.c2)]
+        return w, u, c
+
+    def hom_on(self, w, c, u):
+        return [G.eval_expr(self.meta["hom"], self.m, self._col(w), c + [u], r, self.rows) for r in range(self.rows)]
+
+    def cross_term_challenges(self):
+        return self.c1 + [self.u1] + self.c2 + [1]
+
+    def bytes(self):
+        m = self.m
+        return {"fixed": [mont(c, m) for c in self.fixed], "w1": mont(self.w1, m), "w2": mont(self.w2, m), "e1": mont(self.e1, m),
+                "r": mont([self.r], m), "challenges": mont(self.cross_term_challenges(), m)}
+
+    def domain_bytes(self, w1: bytes, w2, challenges: bytes) -> dict:
+        """oracle_lib.eval_rows domain over (W1s = [w1], W2s = [w2] or [])."""
+        return {"row_size": self.rows, "num_advice": self.meta["num_advice"], "num_lookup": 0, "selectors": [],
+                "fixed": [mont(c, self.m) for c in self.fixed], "w1": [w1], "w2": [w2] if w2 is not None else [],
+                "challenges": challenges}
