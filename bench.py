@@ -273,6 +273,33 @@ def run_ours(args):
 
     # ---- extras: strong-scaling companions (not the headline)
     extras = {}
+    if world > 1:
+        # where a multi-rank step's time goes: every rank's own MSM (no collective), and the exchange + combine alone
+        def local_ms(reps=3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                ck.partial_batch_device([sh.scalars.data_ptr()], n, sh.part.data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        mine_ms = torch.tensor([local_ms()], device=dev, dtype=torch.float64)
+        all_ms = torch.empty(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(all_ms, mine_ms)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            dist.all_gather_into_tensor(sh.gathered, sh.part)
+            combine_partials_device(curve, sh.gathered.data_ptr(), world, 1, 128, local, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        extras["step_breakdown"] = {"rank_msm_ms": [round(float(x), 3) for x in all_ms.cpu().tolist()],
+                                    "exchange_and_combine_ms": round(e0.elapsed_time(e1) / 10, 3),
+                                    "what": "per-rank device time of the rank's own partial MSM (no collective); all_gather of N x 128 B + "
+                                            "combine + 64 B D2H alone (rank 0's clock)"}
     sh.ck.close()
     del sh.bases
     if not args.no_extras:

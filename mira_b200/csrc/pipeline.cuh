@@ -196,7 +196,21 @@ inline int acc_chunk_len(size_t EA) {
   static const int lmin = [] { const char* e = getenv("MIRA_ACC_LMIN"); return e ? atoi(e) : 32; }();
   const unsigned waves = waves_env ? waves_env : (EA < ((size_t)32 << 20) ? 2u : 4u);
   int L = (int)(EA / (148u * 512u * waves));
-  return L < lmin ? lmin : (L > 256 ? 256 : L);
+  L = L < lmin ? lmin : (L > 256 ? 256 : L);
+  // Long lists run many waves of 148 SMs x 4 resident blocks x 128 threads; a last wave that is only partly full runs
+  // at low occupancy (2^24 points: 10.38 waves at L = 256).  Shorten the chunks a little so that the thread count is
+  // just under a whole number of waves (MIRA_ACC_WAVE_FIT=0 turns it off).
+  static const int fit = [] { const char* e = getenv("MIRA_ACC_WAVE_FIT"); return e ? atoi(e) : 1; }();
+  if (fit && L >= 64) {
+    const double per_wave = 148.0 * 4.0 * 128.0;
+    const double w = (double)EA / (L * per_wave);
+    const double target = std::ceil(w);
+    if (target >= 2.0 && w < target - 0.04) {
+      int L2 = (int)std::ceil((double)EA / (target * per_wave - 64.0));
+      if (L2 >= lmin && L2 <= L) L = L2;
+    }
+  }
+  return L;
 }
 
 struct MsmPlan {
@@ -374,12 +388,23 @@ int msm_acc(mira_msm_ctx* ctx, MsmPlan* plan, bool add_mode, int bs, cudaStream_
     const int L = acc_chunk_len(EA);
     uint32_t n_chunks = (uint32_t)((EA + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
+    // MIRA_ACC_PAD_KB (development knob): unused dynamic shared memory per accumulation block, to cap the blocks
+    // per SM and leave room for the sort blocks of the NEXT slice (overlap experiments)
+    static const int pad_kb = [] { const char* e = getenv("MIRA_ACC_PAD_KB"); return e ? atoi(e) : 0; }();
+    if (pad_kb > 0) {
+      static std::once_flag pad_once[64];
+      int dev_id = 0;
+      cudaGetDevice(&dev_id);
+      std::call_once(pad_once[dev_id & 63], [&] {
+        cudaFuncSetAttribute(k_accumulate<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
+      });
+    }
     if (acc_direct)
       k_accumulate<CF, true><<<(n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, nullptr, acc_n, L, acc_points, ctx->buckets.p,
                                                                     (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
     else
-      k_accumulate<CF, false><<<(n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, acc_refs, acc_n, L, acc_points, ctx->buckets.p,
-                                                                     (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
+      k_accumulate<CF, false><<<(n_chunks + 127) / 128, 128, (size_t)(pad_kb > 0 ? pad_kb : 0) * 1024, st>>>(
+          acc_keys, acc_refs, acc_n, L, acc_points, ctx->buckets.p, (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
     uint32_t heavy_cap = n_chunks / HEAVY_CHUNKS + 2;
     if ((rc = ctx->cursor.ensure(((size_t)heavy_cap * 2 + 4) * 4))) return rc;
     uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0], [1] = counts, then the medium and the huge leader lists
@@ -427,7 +452,12 @@ inline int pipe_slices_for(const mira_msm_ctx* ctx, size_t n) {
 }
 inline int pipe_setup(mira_msm_ctx* ctx) {
   if (!ctx->prep_stream) {
-    CU(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+    // MIRA_PREP_PRIO=1: the preparation stream outranks the accumulation, so its (short) sort blocks are placed
+    // ahead of the accumulation blocks still waiting for an SM
+    static const int prio = [] { const char* e = getenv("MIRA_PREP_PRIO"); return e ? atoi(e) : 0; }();
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, prio ? hi : lo));
   }
   for (cudaEvent_t* e : {&ctx->prep_done[0], &ctx->prep_done[1], &ctx->acc_done[0], &ctx->acc_done[1], &ctx->pipe_start})
     if (!*e) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));

@@ -14,6 +14,8 @@
 // HBM traffic per pass: 4 B (hist) + 8 B read + 8 B write per pair.
 #include "ctx.hpp"
 
+#include <cstdlib>
+
 namespace mira_host {
 
 constexpr int RS_BINS = 256;
@@ -256,28 +258,35 @@ __global__ void __launch_bounds__(THREADS) k_radix_scatter(const uint32_t* __res
 }
 
 constexpr int RS_THREADS = MIRA_RS_THREADS;        // the shipped geometry
-constexpr int RS_TILE = RsCfg<RS_THREADS>::TILE;
+constexpr int RS_THREADS_SMALL = 256;              // alternative: smaller blocks that fit onto an SM beside accumulation blocks
+
+// MIRA_RS_THREADS_RT=256 selects the small geometry at run time (development knob for the overlap experiments)
+static int rs_threads_runtime() {
+  static const int v = [] { const char* e = getenv("MIRA_RS_THREADS_RT"); return e && atoi(e) == RS_THREADS_SMALL ? RS_THREADS_SMALL : RS_THREADS; }();
+  return v;
+}
 
 size_t radix_sort_temp_bytes(size_t max_pairs) {
-  size_t n_tiles = (max_pairs + RS_TILE - 1) / RS_TILE;
+  const size_t tile = RsCfg<RS_THREADS_SMALL>::TILE;       // the smaller tile needs the larger histogram
+  size_t n_tiles = (max_pairs + tile - 1) / tile;
   size_t hist = (size_t)RS_BINS * n_tiles;
   size_t sums = (hist + SC_TILE - 1) / SC_TILE + 1;
   return (hist + sums + 64) * 4;
 }
 
-// Sorts the first *n_ptr pairs of (keys_a, vals_a) by the low `key_bits` bits of the key.  Ping-pongs
-// between the a/b buffers; *sorted_in_b tells where the result ends up.  All launches go to `st`.
-int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
-                     size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches) {
+template <int THREADS>
+static int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
+                              size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches) {
+  constexpr int TILE = RsCfg<THREADS>::TILE;
   static std::once_flag attr_once[64];       // the attribute is per device; contexts of several keys may race here
   int dev = 0;
   CU(cudaGetDevice(&dev));
   cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once[dev & 63], [&] {
-    attr_err = cudaFuncSetAttribute(k_radix_scatter<RS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<RS_THREADS>));
+    attr_err = cudaFuncSetAttribute(k_radix_scatter<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<THREADS>));
   });
   CU(attr_err);
-  const uint32_t n_tiles = (uint32_t)((max_pairs + RS_TILE - 1) / RS_TILE);
+  const uint32_t n_tiles = (uint32_t)((max_pairs + TILE - 1) / TILE);
   if (n_tiles == 0) {
     *sorted_in_b = 0;
     return MIRA_OK;
@@ -291,11 +300,11 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   uint32_t *ka = keys_a, *va = vals_a, *kb = keys_b, *vb = vals_b;
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
-    k_radix_hist<RS_THREADS><<<n_tiles, RS_THREADS, 0, st>>>(ka, n_ptr, shift, hist, n_tiles);
+    k_radix_hist<THREADS><<<n_tiles, THREADS, 0, st>>>(ka, n_ptr, shift, hist, n_tiles);
     k_scan_sums<<<n_sums, SC_THREADS, 0, st>>>(hist, hist_n, sums);
     k_scan_top<<<1, SC_THREADS, 0, st>>>(sums, n_sums);
     k_scan_down<<<n_sums, SC_THREADS, 0, st>>>(hist, hist_n, sums);
-    k_radix_scatter<RS_THREADS><<<n_tiles, RS_THREADS, sizeof(RsSmem<RS_THREADS>), st>>>(ka, va, n_ptr, shift, hist, n_tiles, kb, vb);
+    k_radix_scatter<THREADS><<<n_tiles, THREADS, sizeof(RsSmem<THREADS>), st>>>(ka, va, n_ptr, shift, hist, n_tiles, kb, vb);
     if (launches) *launches += 5;
     std::swap(ka, kb);
     std::swap(va, vb);
@@ -303,6 +312,15 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   CU(cudaGetLastError());
   *sorted_in_b = (passes & 1);
   return MIRA_OK;
+}
+
+// Sorts the first *n_ptr pairs of (keys_a, vals_a) by the low `key_bits` bits of the key.  Ping-pongs
+// between the a/b buffers; *sorted_in_b tells where the result ends up.  All launches go to `st`.
+int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
+                     size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches) {
+  if (rs_threads_runtime() == RS_THREADS_SMALL)
+    return radix_sort_pairs_t<RS_THREADS_SMALL>(keys_a, vals_a, keys_b, vals_b, n_ptr, max_pairs, key_bits, temp, st, sorted_in_b, launches);
+  return radix_sort_pairs_t<RS_THREADS>(keys_a, vals_a, keys_b, vals_b, n_ptr, max_pairs, key_bits, temp, st, sorted_in_b, launches);
 }
 
 }  // namespace mira_host
