@@ -591,10 +591,7 @@ def run_fold_step_sharded(args, F):
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if "MIRA_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["MIRA_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
+    setup_nccl_logging()
     dist.init_process_group("nccl", device_id=dev)
     g = F.ShardedGpuFoldStep(args.log_rows, rank, world, device=local)
     gathered = torch.empty(world * g.n_commits * 128, dtype=torch.uint8, device=dev)

@@ -6,30 +6,21 @@
 //
 // The multiplier bodies are generated (tools/gen_field_ptx.py -> field_gen.cuh) as inline PTX
 // whose mad.lo.cc/madc.hi.cc pairs ptxas fuses into IMAD.WIDE.U32[.X]; modulus limbs are
-// immediates.  B200 measured issue rate for IMAD.WIDE.U32 is 32 lanes/clk/SM (profiles/
-// r01_intpipe_microbench.jsonl), which is the roofline denominator of every kernel built on this.
+// immediates.  B200 measured issue rate for IMAD.WIDE.U32 is 32 lanes/clk/SM (profiles/imad_peak.json,
+// r02_modmul_ncu.txt), which is the roofline denominator of every kernel built on this.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "field_gen.cuh"
-#include "field_gen_v2.cuh"
 
-// Multiplier selection (compile time; the Makefile builds the shipped choice, the others exist for A/B timing):
-//   MIRA_MUL_IMPL 0  v1: interleaved product/reduction, 128 wide MACs per product            (field_gen.cuh)
-//                 1  v2: separated schoolbook product + reduction, 128 wide MACs, square 100   (field_gen_v2.cuh)
-//                 2  v2 with one Karatsuba level: 112 wide MACs per product, square 100
-//   MIRA_LAZY_SUB 1  differences of two products share one reduction (xyzz_madd / xyzz_add: y3)
-//   MIRA_DUAL_MUL 1  (v1 only) a*b - c*d as ONE interleaved pass with one reduction: 192 wide MACs instead of 256
-// Measured on B200 at 2^24 points (k_accumulate, ms): v1 34.0 | v2 schoolbook + lazy 36.7 | v2 Karatsuba + lazy 39.3 |
-// v2 Karatsuba 41.6.  Fewer wide MACs did NOT pay: the separated forms add IADD3/MOV traffic and registers (118 -> 158),
-// and ptxas turns part of it into IMAD.MOV/IMAD.IADD on the same pipe.  v1 stays the shipped multiplier.
-#ifndef MIRA_MUL_IMPL
-#define MIRA_MUL_IMPL 0
-#endif
-#ifndef MIRA_LAZY_SUB
-#define MIRA_LAZY_SUB 1
-#endif
+// Multiplier: the interleaved word-serial product of field_gen.cuh (128 wide MACs + 8 IMAD per product), with
+// MIRA_DUAL_MUL a*b +- c*d as ONE interleaved pass under one reduction (192 wide MACs instead of 256).
+// A second generator (separated 16-limb product, optional Karatsuba level, dedicated square, lazy wide subtraction:
+// fewer wide MACs) was measured SLOWER on B200 in round 1 (k_accumulate at 2^24, ms: this one 34.0 | separated
+// schoolbook + lazy 36.7 | Karatsuba + lazy 39.3 | Karatsuba 41.6: the saved MACs came back as IADD3/MOV traffic and
+// registers, 118 -> 158) and has been removed from the tree (git history: field_gen_v2.cuh, tools/gen_field_ptx_v2.py);
+// an FP64-pipe product was measured in round 2 and is no faster either (tools/microbench/fp52.cuh).
 #ifndef MIRA_DUAL_MUL
 #define MIRA_DUAL_MUL 1
 #endif
@@ -116,64 +107,19 @@ __device__ __forceinline__ void mod_add_raw(FrTag, uint32_t (&r)[8], const uint3
 __device__ __forceinline__ void mod_sub_raw(FqTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mod_sub_Fq(r, a, b); }
 __device__ __forceinline__ void mod_sub_raw(FrTag, uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { gen::mod_sub_Fr(r, a, b); }
 
-// ---- v2: 16-limb unreduced products ----------------------------------------------------------------
-template <class F>
-struct Wide {
-  uint32_t v[16];     // < MOD * 2^256
-};
-__device__ __forceinline__ void redc_raw(FqTag, uint32_t (&r)[8], const uint32_t (&t)[16]) { gen2::redc_Fq(r, t); }
-__device__ __forceinline__ void redc_raw(FrTag, uint32_t (&r)[8], const uint32_t (&t)[16]) { gen2::redc_Fr(r, t); }
-__device__ __forceinline__ void wsub_raw(FqTag, uint32_t (&r)[16], const uint32_t (&a)[16], const uint32_t (&b)[16]) { gen2::wsub_Fq(r, a, b); }
-__device__ __forceinline__ void wsub_raw(FrTag, uint32_t (&r)[16], const uint32_t (&a)[16], const uint32_t (&b)[16]) { gen2::wsub_Fr(r, a, b); }
-
-template <class F> __device__ __forceinline__ Wide<F> fe_mul_wide(const Fe<F>& a, const Fe<F>& b) {
-  Wide<F> t;
-#if MIRA_MUL_IMPL == 2
-  gen2::mul_wide_kara(t.v, a.v, b.v);
-#else
-  gen2::mul_wide_school(t.v, a.v, b.v);
-#endif
-  return t;
-}
-template <class F> __device__ __forceinline__ Wide<F> fe_sqr_wide(const Fe<F>& a) {
-  Wide<F> t;
-  gen2::sqr_wide(t.v, a.v);
-  return t;
-}
-// Montgomery reduction: T / 2^256 mod MOD, fully reduced
-template <class F> __device__ __forceinline__ Fe<F> fe_redc(const Wide<F>& t) {
-  Fe<F> r;
-  redc_raw(F{}, r.v, t.v);
-  return r;
-}
-// a - b modulo MOD * 2^256 (still a valid input of fe_redc)
-template <class F> __device__ __forceinline__ Wide<F> wide_sub(const Wide<F>& a, const Wide<F>& b) {
-  Wide<F> r;
-  wsub_raw(F{}, r.v, a.v, b.v);
-  return r;
-}
-
 template <class F> __device__ __forceinline__ Fe<F> fe_mul(const Fe<F>& a, const Fe<F>& b) {
-#if MIRA_MUL_IMPL == 0
   Fe<F> r;
   mont_mul_raw(F{}, r.v, a.v, b.v);
   return r;
-#else
-  return fe_redc(fe_mul_wide(a, b));
-#endif
 }
 template <class F> __device__ __forceinline__ Fe<F> fe_sqr(const Fe<F>& a) {
-#if MIRA_MUL_IMPL == 0
   Fe<F> r;
   mont_sqr_raw(F{}, r.v, a.v);
   return r;
-#else
-  return fe_redc(fe_sqr_wide(a));
-#endif
 }
 // a*b + c*d with ONE reduction
 template <class F> __device__ __forceinline__ Fe<F> fe_mul_add_mul(const Fe<F>& a, const Fe<F>& b, const Fe<F>& c, const Fe<F>& d) {
-#if MIRA_MUL_IMPL == 0 && MIRA_DUAL_MUL
+#if MIRA_DUAL_MUL
   uint32_t bcd[24];
 #pragma unroll
   for (int i = 0; i < 8; i++) { bcd[i] = b.v[i]; bcd[8 + i] = c.v[i]; bcd[16 + i] = d.v[i]; }
@@ -184,11 +130,9 @@ template <class F> __device__ __forceinline__ Fe<F> fe_mul_add_mul(const Fe<F>& 
   return fe_add(fe_mul(a, b), fe_mul(c, d));
 #endif
 }
-// a*b - c*d with ONE reduction when lazy subtraction is enabled
+// a*b - c*d with ONE reduction
 template <class F> __device__ __forceinline__ Fe<F> fe_mul_sub_mul(const Fe<F>& a, const Fe<F>& b, const Fe<F>& c, const Fe<F>& d) {
-#if MIRA_MUL_IMPL != 0 && MIRA_LAZY_SUB
-  return fe_redc(wide_sub(fe_mul_wide(a, b), fe_mul_wide(c, d)));
-#elif MIRA_MUL_IMPL == 0 && MIRA_DUAL_MUL
+#if MIRA_DUAL_MUL
   // a*b + (MOD - c)*d: both products accumulate into one interleaved Montgomery pass
   Fe<F> nc = fe_sub(fe_zero<F>(), c);
   uint32_t bcd[24];
