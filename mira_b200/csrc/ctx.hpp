@@ -72,7 +72,7 @@ struct mira_msm_ctx {
   std::vector<mira_host::Table> tables;
   uint64_t table_clock = 0;
   // workspace (grown on demand, reused across commits)
-  mira_host::DevBuf scalars, cursor, buckets, part_keys, part_pts, red_a, red_b, result;
+  mira_host::DevBuf scalars, cursor, buckets, part_keys, part_pts, red_a, red_b, red_c, red_d, result;
   // Pair-list workspace of one slice: unsorted and sorted (key, ref) arrays, counters, radix-sort scratch.  Two sets, so
   // that slice k+1 can be decomposed and sorted (prep_stream) while slice k is accumulated (pipeline.cuh).
   struct SortBufs {

@@ -253,7 +253,7 @@ void mira_msm_ctx_destroy(mira_msm_ctx* ctx) {
   ctx->gather.release();
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& t : ctx->tables) cudaFree(t.d);
-  for (DevBuf* b : {&ctx->scalars, &ctx->cursor, &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->result,
+  for (DevBuf* b : {&ctx->scalars, &ctx->cursor, &ctx->buckets, &ctx->part_keys, &ctx->part_pts, &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d, &ctx->result,
                     &ctx->pa_a, &ctx->pa_b, &ctx->pa_work})
     b->release();
   for (auto& sb : ctx->sb)

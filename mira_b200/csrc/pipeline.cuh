@@ -486,27 +486,79 @@ int msm_pipeline(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, const 
   return MIRA_OK;
 }
 
+// Chunk width (log2) of a reduction level over n elements; 0 = small enough for the closing k_reduce_chunks pass.
+// MIRA_RED_LEVELS=0 turns the level passes off (the round-1 single pass).
+inline int reduce_level_log_m(uint32_t n) {
+  static const int on = [] { const char* e = getenv("MIRA_RED_LEVELS"); return e ? atoi(e) : 1; }();
+  // measured (profiles/r02_reduce_levels.txt): 2^21 buckets 2.10 -> 1.75 ms, 2^19 0.71 -> 0.71; below that a level
+  // only adds latency (2^16 buckets 0.45 -> 0.52 ms, 2^14 0.30 -> 0.40), so small bucket sets keep the single pass
+  if (!on || n < ((uint32_t)1 << 20)) return 0;
+  return 4;
+}
+
 template <class CF>
 int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt) {
   int rc;
   const uint32_t B = plan->B;
   const unsigned S = (unsigned)plan->n_sets;
-  // buckets per thread: the running sums are a serial chain of 2m full adds per thread, so small bucket sets get a
-  // small m (more, shorter chains: at B = 2^16 the phase was 0.7 ms of pure latency with m = 32) and only the largest
-  // sets, which have the threads to fill the machine anyway, amortise the per-thread weighting over m = 32 buckets
-  uint32_t m = B >> 15;
+  // S = sum_b b * bucket[b].  For large bucket sets (>= 2^20) level passes (k_reduce_level) shrink the array 16x each
+  // with two running sums per chunk and four doublings; the rest goes through k_reduce_chunks, whose per-thread
+  // weighting by a small scalar multiplication is affordable there; every pass leaves partial sums in one array that
+  // a tree sum (k_sum_points) folds.  Sizes first:
+  uint32_t level_n[8], level_chunks[8];
+  int level_log_m[8], n_levels = 0;
+  uint32_t n = B;
+  size_t a_total = 0;
+  while (n_levels < 8) {
+    const int lm = reduce_level_log_m(n);
+    if (!lm) break;
+    const uint32_t chunks = (uint32_t)(((uint64_t)n + (1u << lm) - 1) >> lm);
+    level_n[n_levels] = n; level_chunks[n_levels] = chunks; level_log_m[n_levels] = lm;
+    n_levels++;
+    a_total += chunks;
+    n = chunks - 1;
+  }
+  // closing pass over the remaining n elements: buckets per thread m: the running sums are a serial chain of 2m full
+  // adds per thread, so small sets get a small m (more, shorter chains)
+  uint32_t m = n >> 15;
   m = m < 2 ? 2 : (m > 32 ? 32 : m);
-  if (B < 2) m = 1;
-  uint32_t n_red = (B + m - 1) / m;
-  const size_t a_stride = (size_t)n_red * 128, b_stride = (size_t)(n_red / 128 + 2) * 128;
+  if (n < 2) m = 1;
+  const uint32_t n_red = n ? (n + m - 1) / m : 0;
+  a_total += n_red;
+  const size_t a_stride = (a_total + 1) * 128, b_stride = (size_t)(a_total / 128 + 2) * 128;
+  const size_t y_stride = ((size_t)(n_levels ? level_chunks[0] : 1) + 1) * 128;
   if ((rc = ctx->red_a.ensure(a_stride * S)) || (rc = ctx->red_b.ensure(b_stride * S)) || (rc = ctx->result.ensure((size_t)S * 192 + 256)))
     return rc;
-  k_reduce_chunks<CF><<<dim3((n_red + 127) / 128, S), 128, 0, st>>>(ctx->buckets.p, B, m, ctx->red_a.p, ((size_t)B + 1) * 128, a_stride);
-  plan->launches++;
+  if (n_levels && ((rc = ctx->red_c.ensure(y_stride * S)) || (rc = ctx->red_d.ensure(y_stride * S)))) return rc;
+  // bucket b of set s lives at buckets + s * in_stride + b * 128; element i of the level-0 array is bucket i + 1
+  const char* src_lvl = reinterpret_cast<const char*>(ctx->buckets.p) + 128;
+  size_t src_stride = ((size_t)B + 1) * 128;
+  size_t a_off = 0;
+  for (int l = 0; l < n_levels; l++) {
+    void* next = (l & 1) ? ctx->red_d.p : ctx->red_c.p;
+    k_reduce_level<CF><<<dim3((level_chunks[l] + 127) / 128, S), 128, 0, st>>>(src_lvl, level_n[l], level_log_m[l],
+                                                                               reinterpret_cast<char*>(ctx->red_a.p) + a_off * 128, next,
+                                                                               src_stride, a_stride, y_stride);
+    plan->launches++;
+    a_off += level_chunks[l];
+    src_lvl = reinterpret_cast<const char*>(next);
+    src_stride = y_stride;
+  }
+  if (n_red) {
+    // k_reduce_chunks indexes buckets 1..n: element i of the current array is its "bucket" i + 1
+    k_reduce_chunks<CF><<<dim3((n_red + 127) / 128, S), 128, 0, st>>>(src_lvl - 128, n, m, reinterpret_cast<char*>(ctx->red_a.p) + a_off * 128,
+                                                                      src_stride, a_stride);
+    plan->launches++;
+  }
   void* src = ctx->red_a.p;
   void* dst = ctx->red_b.p;
-  size_t src_stride = a_stride, dst_stride = b_stride;
-  uint32_t cnt = n_red;
+  size_t dst_stride = b_stride;
+  src_stride = a_stride;
+  uint32_t cnt = (uint32_t)a_total;
+  if (cnt == 0) {                 // B == 1 and nothing to weight beyond bucket 1 itself cannot happen (B >= 2); be safe
+    CU(cudaMemsetAsync(ctx->red_a.p, 0, a_stride * S, st));
+    cnt = 1;
+  }
   while (cnt > 1) {
     // few points: one per thread (the serial part of a thread is as slow as a tree level, and the GPU is idle anyway)
     uint32_t per_thread = cnt > ((uint32_t)1 << 16) ? 8 : 1;
