@@ -596,6 +596,8 @@ def run_fold_step_sharded(args, F):
     g = F.ShardedGpuFoldStep(args.log_rows, rank, world, device=local)
     gathered = torch.empty(world * g.n_commits * 128, dtype=torch.uint8, device=dev)
 
+    part_buf = g.partials
+
     def step():
         part = g.step()
         with torch.cuda.stream(g.stream):
@@ -625,6 +627,30 @@ def run_fold_step_sharded(args, F):
     dist.all_gather_into_tensor(all_d, digest)
     same = bool((all_d.view(world, -1) == digest).all().item())
     launches = sum(int(t["ck"].stats()["kernel_launches"]) for t in g.state)
+    # where the step's time goes: every rank's own share (no collective), and the exchange + combine alone
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(g.stream)
+    for _ in range(5):
+        g.step()
+    l1.record(g.stream)
+    torch.cuda.synchronize()
+    mine_ms = torch.tensor([l0.elapsed_time(l1) / 5], device=dev, dtype=torch.float64)
+    all_ms = torch.empty(world, device=dev, dtype=torch.float64)
+    dist.all_gather_into_tensor(all_ms, mine_ms)
+    dist.barrier()
+    torch.cuda.synchronize()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record(g.stream)
+    for _ in range(10):
+        with torch.cuda.stream(g.stream):
+            dist.all_gather_into_tensor(gathered, part_buf)
+        g.combine(gathered, world)
+    x1.record(g.stream)
+    torch.cuda.synchronize()
+    breakdown = {"rank_share_ms": [round(float(x), 3) for x in all_ms.cpu().tolist()],
+                 "exchange_and_combine_ms": round(x0.elapsed_time(x1) / 10, 3)}
     if rank == 0:
         assert same, "ranks disagree on the combined commitments"
         ncommit = g.n_commits
@@ -641,6 +667,7 @@ def run_fold_step_sharded(args, F):
                "clocks": clocks,
                "e2e": None,
                "gpu_launches": (2 * launches + 2 * len(g.state) * 2 + 2) * args.steps * world,
+               "step_breakdown": breakdown,
                "commitments_sha256": __import__("hashlib").sha256(b"".join(res)).hexdigest()}
         print(json.dumps(out), flush=True)
     dist.barrier()

@@ -154,8 +154,10 @@ __device__ __forceinline__ Affine<CF> load_ref(const void* __restrict__ table, u
   return p;
 }
 
+// L2 prefetch distance of the table gather, in entries (0 = off).  Measured at 2^24 points, accumulation phase in ms
+// (profiles/r02_acc_variants.txt): off 31.99 | 2 ahead 31.78 | 6 ahead 32.04; __launch_bounds__(128, 5) 32.27.
 #ifndef MIRA_ACC_PREFETCH
-#define MIRA_ACC_PREFETCH 0
+#define MIRA_ACC_PREFETCH 2
 #endif
 #ifndef MIRA_ACC_MIN_BLOCKS
 #define MIRA_ACC_MIN_BLOCKS 1
