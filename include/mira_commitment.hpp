@@ -68,6 +68,13 @@ class CommitmentKey {
   CommitmentKey(const Affine* bases, size_t n, int device = 0) : n_(n) {
     check(mira_msm_ctx_create(Curve::id, bases, n, /*bases_on_device=*/0, device, &ctx_));
   }
+  // The same key spread over several GPUs of this process (mira_msm_ctx_create_sharded): contiguous point ranges on
+  // `devices`; commit(host vector) runs on all of them and returns the same 64 bytes.  Device-vector methods throw
+  // std::invalid_argument on such a key.
+  CommitmentKey(const Affine* bases, size_t n, const std::vector<int>& devices) : n_(n) {
+    check(mira_msm_ctx_create_sharded(Curve::id, bases, n, devices.data(), devices.size(), &ctx_));
+  }
+  size_t num_devices() const { return mira_msm_ctx_num_devices(ctx_); }
   CommitmentKey(const CommitmentKey&) = delete;
   CommitmentKey& operator=(const CommitmentKey&) = delete;
   CommitmentKey(CommitmentKey&& o) noexcept : ctx_(o.ctx_), n_(o.n_) { o.ctx_ = nullptr; }

@@ -90,27 +90,36 @@ static int sharded_commit(mira_msm_ctx* ctx, const void* scalars, size_t n, void
   std::vector<std::string> errs(G);
   std::vector<std::thread> workers;
   workers.reserve(G);
+  auto run_shard = [&](size_t g, size_t lo, size_t cnt) {
+    mira_msm_ctx* sub = ctx->shards[g];
+    std::lock_guard<std::mutex> l2(sub->mu);
+    cudaError_t e = cudaSetDevice(sub->device);
+    if (e != cudaSuccess) {
+      rcs[g] = MIRA_ERR_CUDA;
+      errs[g] = cudaGetErrorString(e);
+      return;
+    }
+    rcs[g] = ops_for(sub->curve).partial_to_peer(sub, (const char*)scalars + lo * 32, cnt, (char*)ctx->gather.p + g * 128, ctx->device,
+                                                  sub->stream);
+    if (rcs[g]) errs[g] = g_err;       // the error text is thread-local: carry it to the calling thread
+  };
   for (size_t g = 0; g < G; g++) {
     const size_t lo = ctx->shard_lo[g], hi = ctx->shard_lo[g + 1];
     const size_t cnt = n > lo ? std::min(n, hi) - lo : 0;
-    workers.emplace_back([&, g, lo, cnt] {
-      mira_msm_ctx* sub = ctx->shards[g];
-      std::lock_guard<std::mutex> l2(sub->mu);
-      cudaError_t e = cudaSetDevice(sub->device);
-      if (e != cudaSuccess) {
-        rcs[g] = MIRA_ERR_CUDA;
-        errs[g] = cudaGetErrorString(e);
-        return;
-      }
-      rcs[g] = ops_for(sub->curve).partial_to_peer(sub, (const char*)scalars + lo * 32, cnt, (char*)ctx->gather.p + g * 128,
-                                                    ctx->device, sub->stream);
-      if (rcs[g]) errs[g] = g_err;       // the error text is thread-local: carry it to the calling thread
-    });
+    if (g + 1 == G) {
+      run_shard(g, lo, cnt);             // the last range on the calling thread
+      break;
+    }
+    try {
+      workers.emplace_back(run_shard, g, lo, cnt);
+    } catch (const std::exception&) {    // no thread to be had: the range still has to be committed
+      run_shard(g, lo, cnt);
+    }
   }
   for (auto& w : workers) w.join();
+  CU(cudaSetDevice(ctx->device));      // the calling thread ran the last range on that range's device
   for (size_t g = 0; g < G; g++)
     if (rcs[g]) return fail(rcs[g], "shard %zu (device %d): %s", g, ctx->shards[g]->device, errs[g].c_str());
-  CU(cudaSetDevice(ctx->device));
   if ((rc = ops_for(ctx->curve).combine_dev(ctx->gather.p, G, 1, 128, out_affine, ctx->stream))) return rc;
   // stats of the whole commit: pairs and launches summed over the shards, phase times of the slowest
   mira_msm_stats agg{};

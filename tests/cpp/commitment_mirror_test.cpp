@@ -50,6 +50,19 @@ static int run(int curve_id, size_t n, bool gpu) {
     if (e.input_len != n + 1 || e.limit != n) return 8;
     std::printf("curve %d: %s\n", curve_id, e.what());
   }
+  // the same key as three point ranges driven from this one process (mira_msm_ctx_create_sharded; device 0 three times
+  // on a one-GPU box): identical bytes, prefix included; device vectors are refused
+  {
+    mira::CommitmentKey<Curve> sharded(bases.data(), n, std::vector<int>{0, 0, 0});
+    if (sharded.num_devices() != 3 || sharded.len() != n) return 9;
+    if (!(sharded.commit(scalars) == got)) return 10;
+    if (!(sharded.commit(scalars.data(), m) == want)) return 11;
+    try {
+      sharded.commit_device(scalars.data(), 1);
+      return 12;
+    } catch (const std::invalid_argument&) {
+    }
+  }
   std::printf("curve %d: C++ mirror ok (n = %zu)\n", curve_id, n);
   return 0;
 }
