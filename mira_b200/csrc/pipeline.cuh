@@ -488,12 +488,16 @@ int msm_pipeline(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, const 
 
 // Chunk width (log2) of a reduction level over n elements; 0 = small enough for the closing k_reduce_chunks pass.
 // MIRA_RED_LEVELS=0 turns the level passes off (the round-1 single pass).
-inline int reduce_level_log_m(uint32_t n) {
+inline int reduce_level_log_m(uint32_t n, int levels_done) {
   static const int on = [] { const char* e = getenv("MIRA_RED_LEVELS"); return e ? atoi(e) : 1; }();
   // measured (profiles/r02_reduce_levels.txt): 2^21 buckets 2.10 -> 1.75 ms, 2^19 0.71 -> 0.71; below that a level
   // only adds latency (2^16 buckets 0.45 -> 0.52 ms, 2^14 0.30 -> 0.40), so small bucket sets keep the single pass
-  if (!on || n < ((uint32_t)1 << 20)) return 0;
-  return 4;
+  // (ncu, profiles/r02_accumulate_v1.txt: after one level of a 2^21-bucket set the closing pass over the remaining
+  // 131,071 elements still took 0.58 ms against 1.18 ms for the level itself, so a big reduction keeps levelling down
+  // to 2^13 elements)
+  if (!on) return 0;
+  if (levels_done == 0) return n >= ((uint32_t)1 << 20) ? 4 : 0;
+  return n >= ((uint32_t)1 << 13) ? 4 : 0;
 }
 
 template <class CF>
@@ -510,7 +514,7 @@ int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt
   uint32_t n = B;
   size_t a_total = 0;
   while (n_levels < 8) {
-    const int lm = reduce_level_log_m(n);
+    const int lm = reduce_level_log_m(n, n_levels);
     if (!lm) break;
     const uint32_t chunks = (uint32_t)(((uint64_t)n + (1u << lm) - 1) >> lm);
     level_n[n_levels] = n; level_chunks[n_levels] = chunks; level_log_m[n_levels] = lm;
