@@ -488,7 +488,7 @@ int msm_pipeline(mira_msm_ctx* ctx, MsmPlan* plan, const void* d_scalars, const 
 
 // Chunk width (log2) of a reduction level over n elements; 0 = small enough for the closing k_reduce_chunks pass.
 // MIRA_RED_LEVELS=0 turns the level passes off (the round-1 single pass).
-inline int reduce_level_log_m(uint32_t n, int levels_done) {
+inline int reduce_level_log_m(uint32_t n, int levels_done, unsigned n_sets) {
   static const int on = [] { const char* e = getenv("MIRA_RED_LEVELS"); return e ? atoi(e) : 1; }();
   // measured (profiles/r02_reduce_levels.txt): 2^21 buckets 2.10 -> 1.75 ms, 2^19 0.71 -> 0.71; below that a level
   // only adds latency (2^16 buckets 0.45 -> 0.52 ms, 2^14 0.30 -> 0.40), so small bucket sets keep the single pass
@@ -496,7 +496,19 @@ inline int reduce_level_log_m(uint32_t n, int levels_done) {
   // 131,071 elements still took 0.58 ms against 1.18 ms for the level itself, so a big reduction keeps levelling down
   // to 2^13 elements)
   if (!on) return 0;
-  if (levels_done == 0) return n >= ((uint32_t)1 << 20) ? 4 : 0;
+  // MIRA_RED_MIN_LOG: log2 of the total bucket count (all sets of a batched commit) from which the first level pays:
+  // the single pass spends ~370 products per thread on its weighting, which is throughput, not latency, once a batch
+  // of 5-6 sets brings a few hundred thousand threads
+  static const int min_log = [] { const char* e = getenv("MIRA_RED_MIN_LOG"); return e ? atoi(e) : 16; }();
+  static const int min_n_log = [] { const char* e = getenv("MIRA_RED_MIN_N_LOG"); return e ? atoi(e) : 14; }();
+  static const int batch_log_m = [] { const char* e = getenv("MIRA_RED_LOG_M"); return e ? atoi(e) : 0; }();
+  if (levels_done == 0) {
+    if (n_sets == 1) return n >= ((uint32_t)1 << 20) ? 4 : 0;
+    // batched commits (profiles/r02_reduce_levels.txt): 6 x 2^19 points (c = 17) 11.39 -> 9.78 ms, 6 x 2^16 (c = 15)
+    // 2.29 -> 2.09 ms with chunks of 8 (2.18 with 16; the larger sets prefer 16: 9.80 against 9.90)
+    if ((uint64_t)n * n_sets < ((uint64_t)1 << min_log) || n < ((uint32_t)1 << min_n_log)) return 0;
+    return batch_log_m ? batch_log_m : (n < ((uint32_t)1 << 15) ? 3 : 4);
+  }
   return n >= ((uint32_t)1 << 13) ? 4 : 0;
 }
 
@@ -514,7 +526,7 @@ int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt
   uint32_t n = B;
   size_t a_total = 0;
   while (n_levels < 8) {
-    const int lm = reduce_level_log_m(n, n_levels);
+    const int lm = reduce_level_log_m(n, n_levels, S);
     if (!lm) break;
     const uint32_t chunks = (uint32_t)(((uint64_t)n + (1u << lm) - 1) >> lm);
     level_n[n_levels] = n; level_chunks[n_levels] = chunks; level_log_m[n_levels] = lm;

@@ -18,7 +18,8 @@ def child():
     bases = gpu_util.gen_bases_dev(0, 1, nmax)
     ck = CommitmentKey(0, bases, on_device=True)
     stream = torch.cuda.current_stream()
-    out = {"waves": os.environ.get("MIRA_ACC_WAVES", "default"), "lmin": os.environ.get("MIRA_ACC_LMIN", "32")}
+    out = {"waves": os.environ.get("MIRA_ACC_WAVES") or "default", "lmin": os.environ.get("MIRA_ACC_LMIN", "32"),
+           "red_min_log": os.environ.get("MIRA_RED_MIN_LOG", "default")}
 
     def timed(fn, reps=10):
         for _ in range(3):
