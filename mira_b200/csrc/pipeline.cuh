@@ -139,6 +139,7 @@ int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device
                 double* pairs_per_scalar = nullptr) {
   *window = 0;
   if (pairs_per_scalar) *pairs_per_scalar = 0.0;        // 0 = not sampled
+  ctx->sampled_pairs_per_scalar = 0.0;
   if (ctx->forced_window || !ctx->adaptive_window || n < ADAPT_MIN_N) return MIRA_OK;
   int rc;
   const size_t samples = (size_t)ADAPT_CHUNKS * ADAPT_CHUNK_LEN, stride = n / ADAPT_CHUNKS;
@@ -165,10 +166,11 @@ int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device
   for (auto& t : ctx->tables)
     if (t.c >= 6 && t.c <= 24 && t.n_cover >= n && costs[t.c] <= 1.05 * costs[best] && (!keep || costs[t.c] < costs[keep])) keep = t.c;
   *window = keep ? keep : best;
-  if (pairs_per_scalar) {       // non-zero signed digits per scalar the sample predicts for the chosen window
+  {                             // non-zero signed digits per scalar the sample predicts for the chosen window
     double pairs = 0;
     for (int L = 1; L <= 256; L++) pairs += (double)ctx->h_hist[L] * (double)((L + *window - 1) / *window);
-    *pairs_per_scalar = pairs / (double)samples;
+    ctx->sampled_pairs_per_scalar = pairs / (double)samples;
+    if (pairs_per_scalar) *pairs_per_scalar = ctx->sampled_pairs_per_scalar;
   }
   return MIRA_OK;
 }
@@ -218,9 +220,11 @@ struct MsmPlan {
     const uint32_t* skeys = nullptr;
     const uint32_t* srefs = nullptr;
     uint32_t* d_npairs = nullptr;
-    size_t E = 0;                   // host-side upper bound of *d_npairs
+    size_t E = 0;                   // host-side upper bound of *d_npairs (the exact count for sparse vectors)
+    size_t E_chunking = 0;          // pair count the accumulation's chunk length is chosen for
   } prep[2];
   int affine_levels = 0;
+  bool exact_count = false;     // sparse vector: read the pair count back after the digit kernel and size everything from it
   int c = 0, W = 0;
   Table* tab = nullptr;
   uint32_t B = 0;
@@ -264,6 +268,13 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
   }
   CU(cudaMemsetAsync(ctx->buckets.p, 0, bucket_bytes, st));
   plan->c = c; plan->W = W; plan->tab = tab; plan->B = B; plan->max_slice = max_slice; plan->n_sets = n_sets;
+  // A sparse vector (the sample predicts well under W pairs per scalar: witness columns are ~60 % zeros) fills only a
+  // fraction of the n * W upper bound the launches are sized from: the sort would launch mostly empty tiles (2^24
+  // witness-like scalars: 1.10 ms of sort for 18 M pairs, 0.48 ms when sized right).  One 4-byte read-back after the
+  // digit kernel (the host synchronises once more, ~30 us) sizes the sort and the accumulation grid from the real count.
+  static const int exact_on = [] { const char* e = getenv("MIRA_EXACT_COUNT"); return e ? atoi(e) : 1; }();
+  plan->exact_count = exact_on && n_sets == 1 && ctx->sampled_pairs_per_scalar > 0.0 && ctx->sampled_pairs_per_scalar < 0.6 * W;
+  ctx->sampled_pairs_per_scalar = 0.0;          // belongs to the commit that sampled it (pick_window runs right before msm_begin)
   plan->launches = 0; plan->entries = 0;
   return MIRA_OK;
 }
@@ -288,18 +299,30 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
         (uint32_t*)sb.refs.p, d_npairs);
     plan->launches++;
   }
+  size_t E_sort = E;
+  if (plan->exact_count) {
+    uint32_t* h_count = ctx->h_hist + 258;          // pinned
+    CU(cudaMemcpyAsync(h_count, d_npairs, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    E_sort = *h_count ? *h_count : 1;               // an all-zero vector still launches (and finds nothing to do)
+    if (E_sort > E) return fail(MIRA_ERR_CUDA, "pair count %zu exceeds its bound %zu", E_sort, E);
+  }
   if (pt) pt->mark(1);
   // ---- group pairs by bucket: LSD radix sort on the c-bit key
   int in_b = 0;
   int key_bits = c;          // keys are < n_sets * (B + 1)
   while (((uint64_t)1 << key_bits) < (uint64_t)plan->n_sets * (plan->B + 1)) key_bits++;
-  if ((rc = radix_sort_pairs((uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, d_npairs, E,
+  if ((rc = radix_sort_pairs((uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, d_npairs, E_sort,
                              key_bits, sb.tile_sums.p, st, &in_b, &plan->launches)))
     return rc;
   plan->prep[bs].skeys = (const uint32_t*)(in_b ? sb.skeys.p : sb.keys.p);
   plan->prep[bs].srefs = (const uint32_t*)(in_b ? sb.srefs.p : sb.refs.p);
   plan->prep[bs].d_npairs = d_npairs;
-  plan->prep[bs].E = E;
+  plan->prep[bs].E = E_sort;
+  // The chunk length stays the one of the n * W bound: sparse vectors pile most of their pairs into a few buckets, and
+  // every chunk inside such a run leaves a partial sum that the heavy-run kernels add up run by run; shorter chunks
+  // measured slower there (2^24 witness-like scalars: accumulation phase 3.69 ms with L = 256, 4.20 ms with L = 60).
+  plan->prep[bs].E_chunking = E;
   if (pt) pt->mark(2);
   return MIRA_OK;
 }
@@ -385,7 +408,7 @@ int msm_acc(mira_msm_ctx* ctx, MsmPlan* plan, bool add_mode, int bs, cudaStream_
   {
     // Sized from the upper bound n*W; grids cover that bound and surplus threads exit on the device-side pair count.
     const size_t EA = acc_bound;
-    const int L = acc_chunk_len(EA);
+    const int L = acc_chunk_len(acc_direct ? EA : std::max(EA, plan->prep[bs].E_chunking));
     uint32_t n_chunks = (uint32_t)((EA + L - 1) / L);
     if ((rc = ctx->part_keys.ensure((size_t)n_chunks * 8)) || (rc = ctx->part_pts.ensure((size_t)n_chunks * 256))) return rc;
     // MIRA_ACC_PAD_KB (development knob): unused dynamic shared memory per accumulation block, to cap the blocks
