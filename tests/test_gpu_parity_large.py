@@ -184,3 +184,36 @@ def test_single_process_sharded_key_equals_single_device(gpu, curve):
         with pytest.raises(ValueError):
             ck.commit_device(0x1000, 1)                        # a device vector lives on ONE device: not on a sharded key
         ck.close()
+
+
+@pytest.mark.parametrize("curve", [R.BN254, R.GRUMPKIN])
+def test_very_sparse_long_vectors(gpu, curve):
+    """Vectors long enough for the sampled window and the exact-pair-count path (>= 2^18 scalars) with almost nothing in
+    them: all zeros (commitment = identity), a single non-zero scalar where no sample chunk looks, non-zeros only inside
+    the first sampled chunk, and 1 % ones — from device and from host memory."""
+    import numpy as np
+    from mira_b200 import CommitmentKey
+    n = (1 << 18) + 77
+    bases_dev = gpu.gen_bases_dev(curve, 606, n)
+    bases = gpu.to_bytes(bases_dev)
+    ck = CommitmentKey(curve, bases_dev, on_device=True)
+    sm = R.scalar_mod(curve)
+    one = np.frombuffer(R.to_mont_bytes(1, sm), dtype=np.uint8)
+    big = np.frombuffer(R.to_mont_bytes(sm - 2, sm), dtype=np.uint8)
+    rng = np.random.default_rng(17)
+    cases = []
+    z = np.zeros((n, 32), dtype=np.uint8)
+    cases.append(("all zeros", z.copy()))
+    v = z.copy(); v[n - 1] = big
+    cases.append(("one scalar at the very end", v))
+    v = z.copy(); v[:100] = one; v[7] = big
+    cases.append(("non-zeros in the first chunk only", v))
+    v = z.copy(); v[rng.choice(n, n // 100, replace=False)] = one
+    cases.append(("1 % ones", v))
+    for name, v in cases:
+        host = v.tobytes()
+        want = O.commit(curve, bases, host)
+        dev = torch.frombuffer(bytearray(host), dtype=torch.uint8).cuda()
+        assert ck.commit_device(dev.data_ptr(), n) == want, name
+        assert ck.commit(host) == want, name
+    assert O.commit(curve, bases, cases[0][1].tobytes()) == bytes(64)
