@@ -296,8 +296,21 @@ def run_ours(args):
             combine_partials_device(curve, sh.gathered.data_ptr(), world, 1, 128, local, stream.cuda_stream)
         e1.record(stream)
         torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        g0.record(stream)
+        for _ in range(20):
+            dist.all_gather_into_tensor(sh.gathered, sh.part)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            combine_partials_device(curve, sh.gathered.data_ptr(), world, 1, 128, local, stream.cuda_stream)
+        combine_ms = (time.perf_counter() - t0) / 20 * 1e3
         extras["step_breakdown"] = {"rank_msm_ms": [round(float(x), 3) for x in all_ms.cpu().tolist()],
                                     "exchange_and_combine_ms": round(e0.elapsed_time(e1) / 10, 3),
+                                    "all_gather_alone_ms": round(g0.elapsed_time(g1) / 20, 3),
+                                    "combine_alone_ms": round(combine_ms, 3),
                                     "what": "per-rank device time of the rank's own partial MSM (no collective); all_gather of N x 128 B + "
                                             "combine + 64 B D2H alone (rank 0's clock)"}
     sh.ck.close()

@@ -846,35 +846,84 @@ int partial_batch_dev_impl(mira_msm_ctx* ctx, const void* const* d_scalar_sets, 
 }
 
 // out[j] = to_affine( sum over ranks g of partials[g * rank_stride + j * 128] ), j < n_commits; partials on the device
-// (as an all_gather leaves them), results to the host.
+// (as an all_gather leaves them), results to the host.  One warp per commitment: lane g sums ranks g, g + 32, ..., a
+// shuffle tree folds the lanes (log2 instead of n_ranks dependent additions: the call sits on the critical path of
+// every multi-rank step), lane 0 normalises.
 template <class CF>
-__global__ void k_combine_partials(const void* __restrict__ partials, uint32_t n_ranks, size_t rank_stride, void* __restrict__ out_affine) {
-  if (threadIdx.x) return;
+__device__ __forceinline__ Xyzz<CF> xyzz_shfl_down(const Xyzz<CF>& p, int delta) {
+  Xyzz<CF> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], delta);
+    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], delta);
+    r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], delta);
+    r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], delta);
+  }
+  return r;
+}
+template <class CF>
+__global__ void __launch_bounds__(32) k_combine_partials(const void* __restrict__ partials, uint32_t n_ranks, size_t rank_stride,
+                                                         void* __restrict__ out_affine) {
+  const uint32_t lane = threadIdx.x;
   Xyzz<CF> acc = xyzz_identity<CF>();
-  for (uint32_t g = 0; g < n_ranks; g++) {
+  for (uint32_t g = lane; g < n_ranks; g += 32) {
     Xyzz<CF> p = xyzz_load<CF>(reinterpret_cast<const char*>(partials) + (size_t)g * rank_stride + (size_t)blockIdx.x * 128);
     xyzz_add(acc, p);
   }
-  aff_store<CF>(reinterpret_cast<char*>(out_affine) + (size_t)blockIdx.x * 64, xyzz_to_affine(acc));
+  uint32_t top = 1;
+  while (top < n_ranks && top < 32) top <<= 1;
+  for (uint32_t d = top >> 1; d > 0; d >>= 1) {
+    Xyzz<CF> o = xyzz_shfl_down(acc, (int)d);
+    if (lane < d) xyzz_add(acc, o);
+  }
+  if (lane == 0) aff_store<CF>(reinterpret_cast<char*>(out_affine) + (size_t)blockIdx.x * 64, xyzz_to_affine(acc));
+}
+
+// scratch of combine_dev_impl, one per device: a device buffer for the affine results and a page-locked mirror
+struct CombineScratch {
+  void* d = nullptr;
+  void* h = nullptr;
+  size_t cap = 0;
+};
+inline CombineScratch* combine_scratch(int device, size_t bytes, std::mutex** mu_out) {
+  static CombineScratch scratch[64];
+  static std::mutex mu[64];
+  CombineScratch& s = scratch[device & 63];
+  *mu_out = &mu[device & 63];
+  std::lock_guard<std::mutex> lk(**mu_out);
+  if (bytes > s.cap) {
+    if (s.d) cudaFree(s.d);
+    if (s.h) cudaFreeHost(s.h);
+    s.d = s.h = nullptr;
+    s.cap = 0;
+    size_t cap = bytes < 4096 ? 4096 : bytes;
+    if (cudaMalloc(&s.d, cap) != cudaSuccess || cudaMallocHost(&s.h, cap) != cudaSuccess) {
+      cudaGetLastError();
+      if (s.d) cudaFree(s.d);
+      s.d = nullptr;
+      return nullptr;
+    }
+    s.cap = cap;
+  }
+  return &s;
 }
 
 template <class CF>
 int combine_dev_impl(const void* d_partials, size_t n_ranks, size_t n_commits, size_t rank_stride, void* out_affine_host, cudaStream_t st) {
-  void* d = nullptr;
-  CU(cudaMallocAsync(&d, n_commits * 64, st));
-  k_combine_partials<CF><<<(unsigned)n_commits, 32, 0, st>>>(d_partials, (uint32_t)n_ranks, rank_stride, d);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_affine_host, d, n_commits * 64, cudaMemcpyDeviceToHost, st);
-  cudaFreeAsync(d, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return fail(MIRA_ERR_CUDA, "combine failed: %s", cudaGetErrorString(e));
+  int device = 0;
+  CU(cudaGetDevice(&device));
+  std::mutex* mu = nullptr;
+  CombineScratch* s = combine_scratch(device, n_commits * 64, &mu);
+  if (!s) return fail(MIRA_ERR_CUDA, "combine: no scratch memory for %zu commitments", n_commits);
+  std::lock_guard<std::mutex> lk(*mu);          // one combine at a time per device (the scratch is shared)
+  k_combine_partials<CF><<<(unsigned)n_commits, 32, 0, st>>>(d_partials, (uint32_t)n_ranks, rank_stride, s->d);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(s->h, s->d, n_commits * 64, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(out_affine_host, s->h, n_commits * 64);
   return MIRA_OK;
 }
 
-// prepare(n): the table the size-only heuristic picks.  prepare_for(scalars, n): the table the ADAPTIVE path will pick
-// for vectors that look like `scalars` (a sample decides; sparse witness columns want a much narrower window than
-// choose_window(n)), so that the first real commit of such a vector does not build a multi-gigabyte table inside its
-// timed region.
 // One shard of a single-process multi-GPU commit (mira_msm_ctx_create_sharded): this device's slice of the HOST scalar
 // vector through the ordinary host-buffer pipeline, then the 128-byte XYZZ partial sum straight from this device's
 // memory into the gather buffer on the combining device (peer copy: NVLink when peer access is enabled, staged by the
