@@ -17,7 +17,9 @@
 // RESULT on B200 (profiles/r02_modmul_microbench.jsonl, profiles/r02_modmul_ncu.txt): 160 FP64 + 159 ALU + 28 other
 // instructions per product; 6.0-6.2e10 products/s against 6.5e10 for the IMAD.WIDE product (sqr 7.1e10 vs 6.5e10):
 // FP64 and ALU pipes both sit at ~52 %, issue at 56 % (math-pipe-throttle, dispatch and fixed-latency waits with 4
-// warps per scheduler) — no faster than the integer product, so the shipped multiplier stays IMAD.WIDE.
+// warps per scheduler) — no faster than the integer product, so the shipped multiplier stays IMAD.WIDE.  Warps running
+// this product beside warps running the IMAD product on the same SM do not add up either (./modmul mix,
+// profiles/r02_modmul_mixed_warps.jsonl: the combined rate never exceeds IMAD.WIDE alone).
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -93,6 +93,103 @@ __global__ void __launch_bounds__(128) k_dfma(uint32_t* out, int iters, Clk* clk
   if (threadIdx.x == 0) clk[blockIdx.x] = Clk{c0, c1, t0, t1};
 }
 
+// ---- heterogeneous warps: NI of the block's 4 warps run the IMAD.WIDE product, the others the FP64-pipe product, at
+// the same time on the same SM.  Do the two pipes add up?  (iters_i / iters_d are chosen by the host so that both
+// kinds finish together; per-kind clocks come back through clk[2 * block + kind].)
+template <int NI>
+__global__ void __launch_bounds__(128) k_mix(uint32_t* out, int iters_i, int iters_d, Clk* clk) {
+  uint64_t s = 0x1234567ull + blockIdx.x * 131ull + threadIdx.x;
+  const int warp = threadIdx.x >> 5;
+  uint32_t acc = 0;
+  if (warp < NI) {
+    Fe<FqTag> x[2], y[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) { x[k] = rnd_fe(s); y[k] = rnd_fe(s); }
+    long long c0 = clock64(); unsigned long long t0 = gtime();
+#pragma unroll 1
+    for (int i = 0; i < iters_i; i++) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) x[k] = fe_mul(x[k], y[k]);
+    }
+    long long c1 = clock64(); unsigned long long t1 = gtime();
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc ^= x[k].v[i];
+    if (threadIdx.x == 0) clk[2 * blockIdx.x] = Clk{c0, c1, t0, t1};
+  } else {
+    Fd<FqTag> x[2], y[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) { x[k] = fd_from_std(rnd_fe(s)); y[k] = fd_from_std(rnd_fe(s)); }
+    long long c0 = clock64(); unsigned long long t0 = gtime();
+#pragma unroll 1
+    for (int i = 0; i < iters_d; i++) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) x[k] = fd_mul(x[k], y[k]);
+    }
+    long long c1 = clock64(); unsigned long long t1 = gtime();
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      Fe<FqTag> r = fd_to_std(x[k]);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc ^= r.v[i];
+    }
+    if (threadIdx.x == 96) clk[2 * blockIdx.x + 1] = Clk{c0, c1, t0, t1};
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <int NI>
+static void run_mix(int sms, int bps) {
+  const int blocks = sms * bps;
+  uint32_t* out; Clk* clk;
+  CK(cudaMalloc(&out, (size_t)blocks * 128 * 4)); CK(cudaMalloc(&clk, 2 * blocks * sizeof(Clk)));
+  std::vector<Clk> h(2 * blocks);
+  auto kind_ns = [&](int kind) {
+    double ns = 0;
+    for (int b = 0; b < blocks; b++) ns += (double)(h[2 * b + kind].t1 - h[2 * b + kind].t0);
+    return ns / blocks;
+  };
+  // calibrate each kind alone at this geometry (the other kind's warps idle), then run both for ~150 ms
+  int it_i = 20000, it_d = 20000;
+  k_mix<NI><<<blocks, 128>>>(out, it_i, 0, clk); CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h.data(), clk, 2 * blocks * sizeof(Clk), cudaMemcpyDeviceToHost));
+  const double ns_i = NI > 0 ? kind_ns(0) / it_i : 1.0;
+  k_mix<NI><<<blocks, 128>>>(out, 0, it_d, clk); CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h.data(), clk, 2 * blocks * sizeof(Clk), cudaMemcpyDeviceToHost));
+  const double ns_d = NI < 4 ? kind_ns(1) / it_d : 1.0;
+  // co-running slows both: start from the solo rates, then rebalance once from the measured co-running rates
+  it_i = NI > 0 ? (int)(1.5e8 / ns_i) : 0;
+  it_d = NI < 4 ? (int)(1.5e8 / ns_d) : 0;
+  double rate_i = 0, rate_d = 0, ms_evt = 0;
+  int it_i_last = 0, it_d_last = 0;
+  for (int round = 0; round < 4; round++) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    k_mix<NI><<<blocks, 128>>>(out, it_i, it_d, clk);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms_evt = ms;
+    it_i_last = it_i; it_d_last = it_d;
+    CK(cudaMemcpy(h.data(), clk, 2 * blocks * sizeof(Clk), cudaMemcpyDeviceToHost));
+    const double t_i = NI > 0 ? kind_ns(0) : 0, t_d = NI < 4 ? kind_ns(1) : 0;
+    rate_i = NI > 0 ? 2.0 * it_i * blocks * 32.0 * NI / (t_i * 1e-9) : 0;           // modmul/s while the IMAD warps ran
+    rate_d = NI < 4 ? 2.0 * it_d * blocks * 32.0 * (4 - NI) / (t_d * 1e-9) : 0;
+    if (NI > 0 && NI < 4) {                    // make both kinds take the same time
+      const double target = 0.5 * (t_i + t_d);
+      it_i = (int)(it_i * target / t_i);
+      it_d = (int)(it_d * target / t_d);
+    }
+  }
+  // whole-kernel accounting (CUDA events): every product of either kind over the kernel's duration -- a lower bound of
+  // the combined rate (the per-warp clocks above only balance the two iteration counts; warps do not finish together)
+  const double tot_i = 2.0 * it_i_last * blocks * 32.0 * NI, tot_d = 2.0 * it_d_last * blocks * 32.0 * (4 - NI);
+  printf("{\"test\": \"mixed warps: %d IMAD + %d FP64 of 4 per block\", \"warps_per_sm\": %d, \"imad_modmul_per_s\": %.4e, "
+         "\"fp52_modmul_per_s\": %.4e, \"sum_per_s\": %.4e, \"ms_events\": %.1f, \"per_warp_clock_rates\": [%.3e, %.3e]}\n",
+         NI, 4 - NI, bps * 4, tot_i / (ms_evt * 1e-3), tot_d / (ms_evt * 1e-3), (tot_i + tot_d) / (ms_evt * 1e-3), ms_evt, rate_i, rate_d);
+  fflush(stdout);
+  CK(cudaFree(out)); CK(cudaFree(clk));
+}
+
 // correctness on the device: fp52 path == IMAD path, bit for bit, over random operands and a dependent chain
 __global__ void k_check(unsigned long long* mismatches, int rounds) {
   uint64_t s = 0xabcdefull + (blockIdx.x * blockDim.x + threadIdx.x) * 7919ull;
@@ -216,6 +313,16 @@ static void run(const char* name, const char* unit, double units_per_thread_iter
 int main(int argc, char** argv) {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   const int sms = p.multiProcessorCount;
+  if (argc > 1 && !strcmp(argv[1], "mix")) {      // do the IMAD and FP64 products add up when they share an SM?
+    for (int bps : {2, 4}) {
+      run_mix<4>(sms, bps);
+      run_mix<3>(sms, bps);
+      run_mix<2>(sms, bps);
+      run_mix<1>(sms, bps);
+      run_mix<0>(sms, bps);
+    }
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "ncu")) {      // one short launch of each product kernel, for ncu --set full
     uint32_t* out; Clk* clk;
     CK(cudaMalloc(&out, (size_t)sms * 4 * 128 * 4)); CK(cudaMalloc(&clk, sms * 4 * sizeof(Clk)));
