@@ -6,6 +6,7 @@
 #include "ctx.hpp"
 #include "msm_kernels.cuh"
 #include "affine_levels.cuh"
+#include "coop.cuh"
 #include "testgen.cuh"
 
 namespace mira_host {
@@ -522,13 +523,14 @@ inline int reduce_level_log_m(uint32_t n, int levels_done, unsigned n_sets) {
   // MIRA_RED_MIN_LOG: log2 of the total bucket count (all sets of a batched commit) from which the first level pays:
   // the single pass spends ~370 products per thread on its weighting, which is throughput, not latency, once a batch
   // of 5-6 sets brings a few hundred thousand threads
-  static const int min_log = [] { const char* e = getenv("MIRA_RED_MIN_LOG"); return e ? atoi(e) : 16; }();
+  static const int min_log = [] { const char* e = getenv("MIRA_RED_MIN_LOG"); return e ? atoi(e) : 17; }();
   static const int min_n_log = [] { const char* e = getenv("MIRA_RED_MIN_N_LOG"); return e ? atoi(e) : 14; }();
   static const int batch_log_m = [] { const char* e = getenv("MIRA_RED_LOG_M"); return e ? atoi(e) : 0; }();
   if (levels_done == 0) {
     if (n_sets == 1) return n >= ((uint32_t)1 << 20) ? 4 : 0;
     // batched commits (profiles/r02_reduce_levels.txt): 6 x 2^19 points (c = 17) 11.39 -> 9.78 ms, 6 x 2^16 (c = 15)
-    // 2.29 -> 2.09 ms with chunks of 8 (2.18 with 16; the larger sets prefer 16: 9.80 against 9.90)
+    // 2.29 -> 2.09 ms with chunks of 8 (2.18 with 16; the larger sets prefer 16: 9.80 against 9.90); below 2^17 buckets in
+    // all the cooperative kernels (coop.cuh) are a little faster still (6 x 2^16 points: 2.04 ms)
     if ((uint64_t)n * n_sets < ((uint64_t)1 << min_log) || n < ((uint32_t)1 << min_n_log)) return 0;
     return batch_log_m ? batch_log_m : (n < ((uint32_t)1 << 15) ? 3 : 4);
   }
@@ -556,6 +558,39 @@ int msm_finish(mira_msm_ctx* ctx, MsmPlan* plan, cudaStream_t st, PhaseTimer* pt
     n_levels++;
     a_total += chunks;
     n = chunks - 1;
+  }
+  // Small bucket sets (no level pass, at most 2^18 buckets in all): the reduction is a chain of dependent additions on
+  // an idle GPU, so it runs on the cooperative kernels of coop.cuh (four warps per addition, ~3x lower latency per
+  // group operation): one launch of at most 256 blocks — every lane owns m buckets, m chosen so that one wave covers
+  // them — and one launch that sums the blocks' results.  MIRA_RED_COOP=0 keeps the round-1 kernels.
+  static const int coop_on = [] { const char* e = getenv("MIRA_RED_COOP"); return e ? atoi(e) : 1; }();
+  static const int coop_max_log = [] { const char* e = getenv("MIRA_RED_COOP_MAX_LOG"); return e ? atoi(e) : 18; }();
+  if (coop_on && n_levels == 0 && B >= 2 && (uint64_t)B * S <= ((uint64_t)1 << coop_max_log)) {
+    uint32_t mc = 2;
+    while ((uint64_t)mc * 8192 < (uint64_t)B * S) mc <<= 1;
+    const uint32_t n_lanes = (B + mc - 1) / mc, blocks = (n_lanes + 31) / 32;
+    const size_t ca_stride = (size_t)(blocks + 1) * 128;
+    if ((rc = ctx->red_a.ensure(ca_stride * S)) || (rc = ctx->red_b.ensure((size_t)256 * S)) || (rc = ctx->result.ensure((size_t)S * 192 + 256)))
+      return rc;
+    k_reduce_coop<CF><<<dim3(blocks, S), COOP_THREADS, 0, st>>>(ctx->buckets.p, B, mc, ctx->red_a.p, ((size_t)B + 1) * 128, ca_stride);
+    plan->launches++;
+    const void* fin = ctx->red_a.p;
+    size_t fin_stride = ca_stride;
+    if (blocks > 1) {
+      k_sum_coop<CF><<<dim3(1, S), COOP_THREADS, 0, st>>>(ctx->red_a.p, blocks, (blocks + 31) / 32, ctx->red_b.p, ca_stride, 256);
+      plan->launches++;
+      fin = ctx->red_b.p;
+      fin_stride = 256;
+    }
+    CU(cudaMemcpy2DAsync(ctx->result.p, 128, fin, fin_stride, 128, S, cudaMemcpyDeviceToDevice, st));
+    if (pt) pt->mark(4);
+    CU(cudaGetLastError());
+    ctx->stats.window_bits = plan->c;
+    ctx->stats.windows = plan->W;
+    ctx->stats.entries = plan->entries;
+    ctx->stats.buckets = B;
+    ctx->stats.kernel_launches = plan->launches;
+    return MIRA_OK;
   }
   // closing pass over the remaining n elements: buckets per thread m: the running sums are a serial chain of 2m full
   // adds per thread, so small sets get a small m (more, shorter chains)
