@@ -125,7 +125,8 @@ inline const CurveOps& ops_for(int curve) { return curve == MIRA_BN254_G1 ? OPS_
 // device radix sort of (key, ref) pairs (sort.cu)
 size_t radix_sort_temp_bytes(size_t max_pairs);
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
-                     size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches);
+                     size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches,
+                     int first_pass = 0);
 
 // field test hook (field_test.cu)
 int test_field_op_dev(int field, int op, const void* a_dev, const void* b_dev, size_t n, void* out_dev);

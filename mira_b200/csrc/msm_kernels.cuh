@@ -115,6 +115,139 @@ __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ 
   }
 }
 
+// ---- digits fused with the FIRST radix pass (round 2) ----------------------------------------------------------
+// The LSD sort's first pass needs no stability (the order the digit kernel emits pairs in carries no meaning), so the
+// digit kernel can place every pair straight into the 256 bins of the key's low byte instead of writing a compacted
+// list that the first pass re-reads, histograms and scatters.  Three launches:
+//   k_digit_hist     the 256-bin histogram of all pairs' low key bytes (scalars re-read in the scatter: 32 B per
+//                    scalar, against the 8 B per PAIR, read and written, of the pass it replaces);
+//   k_digit_scan     exclusive scan of the 256 counts -> per-bin cursors; the total is the pair count (*n_out);
+//   k_digits_scatter a block decomposes `spb` scalars, ranks its pairs by bin with shared-memory atomics, reserves one
+//                    range per bin with a global atomicAdd on that bin's cursor and streams the pairs out bin by bin
+//                    (runs of ~spb * W / 256 pairs).
+// At 2^24 points: digits 0.71 + first pass 1.64 ms -> see DESIGN.md section 6.  Block-to-block order inside a bin
+// depends on the atomics' arrival order; the commitment does not (group addition is commutative and the result is
+// normalised), and the later passes are stable.
+constexpr int DS_THREADS = 256;
+constexpr int DS_CAP = 6144;               // pairs staged per block (48 KiB of keys + refs)
+constexpr int DS_SPB_MAX = 512;            // scalars per block
+
+__host__ __device__ inline uint32_t ds_scalars_per_block(int W) {
+  uint32_t spb = (uint32_t)DS_CAP / (uint32_t)W;
+  spb &= ~31u;
+  return spb > (uint32_t)DS_SPB_MAX ? (uint32_t)DS_SPB_MAX : (spb < 32u ? 32u : spb);
+}
+
+template <class SF>
+__global__ void __launch_bounds__(DS_THREADS) k_digit_hist(const void* __restrict__ scalars, uint32_t n, int c, int W, uint32_t key_offset,
+                                                           uint32_t* __restrict__ g_hist) {
+  __shared__ uint32_t sh[256];
+  __shared__ uint32_t sm_sc[DS_THREADS * 9];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t* sc = sm_sc + threadIdx.x * 9;
+  for (uint32_t i = blockIdx.x * DS_THREADS + threadIdx.x; i < n; i += gridDim.x * DS_THREADS) {
+    Fe<SF> s = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + (size_t)i * 32));
+#pragma unroll
+    for (int k = 0; k < 8; k++) sc[k] = s.v[k];
+    uint32_t carry = 0, neg;
+    for (int j = 0; j < W; j++) {
+      uint32_t d = signed_digit(sc, j, c, carry, neg);
+      if (d) atomicAdd(&sh[(key_offset + d) & 0xffu], 1u);
+    }
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&g_hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// exclusive scan of 256 counts by one block of 256 threads; returns the thread's exclusive prefix, `total` = sum
+__device__ __forceinline__ uint32_t ds_scan256(uint32_t v, uint32_t* tmp8, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) tmp8[warp] = x;
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < DS_THREADS / 32; w++) {
+    uint32_t t = tmp8[w];
+    if (w < warp) off += t;
+    tot += t;
+  }
+  total = tot;
+  __syncthreads();
+  return off + x - v;
+}
+
+static __global__ void __launch_bounds__(DS_THREADS) k_digit_scan(const uint32_t* __restrict__ g_hist, uint32_t* __restrict__ g_cursor,
+                                                           uint32_t* __restrict__ n_out) {
+  __shared__ uint32_t tmp[8];
+  uint32_t total;
+  uint32_t ex = ds_scan256(g_hist[threadIdx.x], tmp, total);
+  g_cursor[threadIdx.x] = ex;
+  if (threadIdx.x == 0) *n_out = total;
+}
+
+template <class SF>
+__global__ void __launch_bounds__(DS_THREADS) k_digits_scatter(const void* __restrict__ scalars, uint32_t n, uint32_t first, int c, int W,
+                                                               uint32_t n_cover, uint32_t key_offset, uint32_t spb,
+                                                               uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ out_keys,
+                                                               uint32_t* __restrict__ out_refs) {
+  extern __shared__ uint32_t ds_dyn[];
+  uint32_t* sc_all = ds_dyn;                       // [spb][9] canonical limbs
+  uint32_t* st_keys = ds_dyn + spb * 9;            // [spb * W] pairs grouped by bin
+  uint32_t* st_refs = st_keys + spb * (uint32_t)W;
+  __shared__ uint32_t cnt[256], dstart[256], gbase[256], tmp[8];
+  const uint32_t base_i = blockIdx.x * spb;
+  const uint32_t cnt_i = n - base_i < spb ? n - base_i : spb;
+  cnt[threadIdx.x] = 0;
+  for (uint32_t s = threadIdx.x; s < cnt_i; s += DS_THREADS) {
+    Fe<SF> v = fe_to_canonical(fe_load<SF>(reinterpret_cast<const char*>(scalars) + (size_t)(base_i + s) * 32));
+#pragma unroll
+    for (int k = 0; k < 8; k++) sc_all[s * 9 + k] = v.v[k];
+  }
+  __syncthreads();
+  for (uint32_t s = threadIdx.x; s < cnt_i; s += DS_THREADS) {
+    uint32_t carry = 0, neg;
+    for (int j = 0; j < W; j++) {
+      uint32_t d = signed_digit(sc_all + s * 9, j, c, carry, neg);
+      if (d) atomicAdd(&cnt[(key_offset + d) & 0xffu], 1u);
+    }
+  }
+  __syncthreads();
+  const uint32_t mine = cnt[threadIdx.x];
+  uint32_t total;
+  const uint32_t ex = ds_scan256(mine, tmp, total);
+  dstart[threadIdx.x] = ex;
+  gbase[threadIdx.x] = mine ? atomicAdd(&g_cursor[threadIdx.x], mine) : 0u;
+  cnt[threadIdx.x] = ex;                           // from here on: the bin's next free staging slot
+  __syncthreads();
+  for (uint32_t s = threadIdx.x; s < cnt_i; s += DS_THREADS) {
+    uint32_t carry = 0, neg;
+    for (int j = 0; j < W; j++) {
+      uint32_t d = signed_digit(sc_all + s * 9, j, c, carry, neg);
+      if (d) {
+        const uint32_t key = key_offset + d;
+        const uint32_t q = atomicAdd(&cnt[key & 0xffu], 1u);
+        st_keys[q] = key;
+        st_refs[q] = ((uint32_t)j * n_cover + first + base_i + s) | neg;     // `scalars` is the slice starting at key index `first`
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t q = threadIdx.x; q < total; q += DS_THREADS) {
+    const uint32_t key = st_keys[q];
+    const uint32_t b = key & 0xffu;
+    const uint32_t dst = gbase[b] + (q - dstart[b]);
+    out_keys[dst] = key;
+    out_refs[dst] = st_refs[q];
+  }
+}
+
 // Bit-length histogram of a SAMPLE of the scalars (n_chunks chunks of chunk_len consecutive scalars, `stride` apart):
 // hist[L] += 1 for every sampled scalar whose canonical value has bit length L (0 for zero).  Feeds
 // choose_window_sampled.  `src_stride` = distance between chunks in the source, in scalars.

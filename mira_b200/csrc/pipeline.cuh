@@ -254,7 +254,7 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
   for (int b = 0; b < n_bufsets; b++) {
     auto& sb = ctx->sb[b];
     if ((rc = sb.keys.ensure(E * 4 + 16)) || (rc = sb.refs.ensure(E * 4 + 16)) || (rc = sb.skeys.ensure(E * 4 + 16)) ||
-        (rc = sb.srefs.ensure(E * 4 + 16)) || (rc = sb.counts.ensure(64)) || (rc = sb.tile_sums.ensure(radix_sort_temp_bytes(E))))
+        (rc = sb.srefs.ensure(E * 4 + 16)) || (rc = sb.counts.ensure(4096)) || (rc = sb.tile_sums.ensure(radix_sort_temp_bytes(E))))
       return rc;
   }
   if ((rc = ctx->buckets.ensure(bucket_bytes))) return rc;
@@ -291,14 +291,34 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
   const size_t E = n * (size_t)W * (size_t)plan->n_sets;
   uint32_t* d_npairs = (uint32_t*)sb.counts.p;     // number of (bucket, ref) pairs, produced on the device
   if (pt) pt->mark(0);
-  // ---- digits (compacted pair list)
-  CU(cudaMemsetAsync(d_npairs, 0, 4, st));
+  // ---- digits.  Default (round 2): fused with the sort's first pass — histogram of the low key byte, scan, then the
+  // digit kernel scatters its pairs into the 256 bins (k_digits_scatter).  MIRA_FUSED_DIGITS=0 keeps the compacted
+  // list + full sort of round 1 (A/B measurements).
+  // Sparse vectors (exact_count: the sample predicts well under W pairs per scalar) keep the compacted list: their
+  // sort is cheap because the pairs are few, and the fused form decomposes every scalar three times instead of twice
+  // (2^24 witness-like scalars: 5.36 ms against 6.13 ms fused).
+  static const int fused_env = [] { const char* e = getenv("MIRA_FUSED_DIGITS"); return e ? atoi(e) : 1; }();
+  const bool fused_on = fused_env == 2 || (fused_env == 1 && !plan->exact_count);
   if (!add_mode) CU(cudaMemsetAsync((char*)sb.counts.p + 48, 0, 8, st));      // affine additions of this commit
-  for (int s = 0; s < plan->n_sets; s++) {
-    k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
-        d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), (uint32_t*)sb.keys.p,
-        (uint32_t*)sb.refs.p, d_npairs);
+  uint32_t* d_hist = (uint32_t*)((char*)sb.counts.p + 1024);                  // [256] low-byte histogram
+  uint32_t* d_cursor = (uint32_t*)((char*)sb.counts.p + 2048);                // [256] next free slot of each bin
+  if (fused_on) {
+    CU(cudaMemsetAsync(d_hist, 0, 1024, st));
+    const unsigned hist_blocks = (unsigned)std::min<size_t>((n + DS_THREADS - 1) / DS_THREADS, 148 * 8);
+    for (int s = 0; s < plan->n_sets; s++) {
+      k_digit_hist<SF><<<hist_blocks, DS_THREADS, 0, st>>>(d_scalar_sets[s], (uint32_t)n, c, W, (uint32_t)s * (plan->B + 1), d_hist);
+      plan->launches++;
+    }
+    k_digit_scan<<<1, DS_THREADS, 0, st>>>(d_hist, d_cursor, d_npairs);
     plan->launches++;
+  } else {
+    CU(cudaMemsetAsync(d_npairs, 0, 4, st));
+    for (int s = 0; s < plan->n_sets; s++) {
+      k_digits<SF><<<(unsigned)((n + DG_THREADS - 1) / DG_THREADS), DG_THREADS, (size_t)W * DG_WARPS * 4, st>>>(
+          d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), (uint32_t*)sb.keys.p,
+          (uint32_t*)sb.refs.p, d_npairs);
+      plan->launches++;
+    }
   }
   size_t E_sort = E;
   if (plan->exact_count) {
@@ -308,14 +328,38 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
     E_sort = *h_count ? *h_count : 1;               // an all-zero vector still launches (and finds nothing to do)
     if (E_sort > E) return fail(MIRA_ERR_CUDA, "pair count %zu exceeds its bound %zu", E_sort, E);
   }
-  if (pt) pt->mark(1);
-  // ---- group pairs by bucket: LSD radix sort on the c-bit key
-  int in_b = 0;
   int key_bits = c;          // keys are < n_sets * (B + 1)
   while (((uint64_t)1 << key_bits) < (uint64_t)plan->n_sets * (plan->B + 1)) key_bits++;
-  if ((rc = radix_sort_pairs((uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, d_npairs, E_sort,
-                             key_bits, sb.tile_sums.p, st, &in_b, &plan->launches)))
-    return rc;
+  int in_b = 0;
+  if (fused_on) {
+    const uint32_t spb = ds_scalars_per_block(W);
+    const size_t dyn = (size_t)spb * 9 * 4 + (size_t)spb * W * 8;
+    static std::once_flag ds_once[64];
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    std::call_once(ds_once[dev_id & 63], [&] {
+      cudaFuncSetAttribute(k_digits_scatter<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SPB_MAX * 9 * 4 + DS_CAP * 8);
+    });
+    for (int s = 0; s < plan->n_sets; s++) {
+      k_digits_scatter<SF><<<(unsigned)((n + spb - 1) / spb), DS_THREADS, dyn, st>>>(
+          d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), spb, d_cursor,
+          (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p);
+      plan->launches++;
+    }
+    if (pt) pt->mark(1);
+    // ---- the remaining passes (bit 8 up) of the LSD radix sort, from the s-buffers into the plain ones and back
+    int in_plain = 0;
+    if ((rc = radix_sort_pairs((uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, (uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, d_npairs, E_sort,
+                               key_bits, sb.tile_sums.p, st, &in_plain, &plan->launches, 1)))
+      return rc;
+    in_b = !in_plain;
+  } else {
+    if (pt) pt->mark(1);
+    // ---- group pairs by bucket: LSD radix sort on the c-bit key
+    if ((rc = radix_sort_pairs((uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, d_npairs, E_sort,
+                               key_bits, sb.tile_sums.p, st, &in_b, &plan->launches)))
+      return rc;
+  }
   plan->prep[bs].skeys = (const uint32_t*)(in_b ? sb.skeys.p : sb.keys.p);
   plan->prep[bs].srefs = (const uint32_t*)(in_b ? sb.srefs.p : sb.refs.p);
   plan->prep[bs].d_npairs = d_npairs;

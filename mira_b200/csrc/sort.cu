@@ -276,7 +276,8 @@ size_t radix_sort_temp_bytes(size_t max_pairs) {
 
 template <int THREADS>
 static int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
-                              size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches) {
+                              size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches,
+                              int first_pass) {
   constexpr int TILE = RsCfg<THREADS>::TILE;
   static std::once_flag attr_once[64];       // the attribute is per device; contexts of several keys may race here
   int dev = 0;
@@ -298,7 +299,7 @@ static int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
   int passes = (key_bits + 7) / 8;
   if (passes < 1) passes = 1;
   uint32_t *ka = keys_a, *va = vals_a, *kb = keys_b, *vb = vals_b;
-  for (int p = 0; p < passes; p++) {
+  for (int p = first_pass; p < passes; p++) {
     int shift = 8 * p;
     k_radix_hist<THREADS><<<n_tiles, THREADS, 0, st>>>(ka, n_ptr, shift, hist, n_tiles);
     k_scan_sums<<<n_sums, SC_THREADS, 0, st>>>(hist, hist_n, sums);
@@ -310,17 +311,19 @@ static int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
     std::swap(va, vb);
   }
   CU(cudaGetLastError());
-  *sorted_in_b = (passes & 1);
+  *sorted_in_b = passes > first_pass ? ((passes - first_pass) & 1) : 0;
   return MIRA_OK;
 }
 
 // Sorts the first *n_ptr pairs of (keys_a, vals_a) by the low `key_bits` bits of the key.  Ping-pongs
 // between the a/b buffers; *sorted_in_b tells where the result ends up.  All launches go to `st`.
+// first_pass = 1: the pairs are already grouped by the key's low byte (the digit kernel's fused first pass,
+// msm_kernels.cuh: k_digits_scatter), so only the passes from bit 8 up are run.
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, const uint32_t* n_ptr,
-                     size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches) {
+                     size_t max_pairs, int key_bits, void* temp, cudaStream_t st, int* sorted_in_b, uint64_t* launches, int first_pass) {
   if (rs_threads_runtime() == RS_THREADS_SMALL)
-    return radix_sort_pairs_t<RS_THREADS_SMALL>(keys_a, vals_a, keys_b, vals_b, n_ptr, max_pairs, key_bits, temp, st, sorted_in_b, launches);
-  return radix_sort_pairs_t<RS_THREADS>(keys_a, vals_a, keys_b, vals_b, n_ptr, max_pairs, key_bits, temp, st, sorted_in_b, launches);
+    return radix_sort_pairs_t<RS_THREADS_SMALL>(keys_a, vals_a, keys_b, vals_b, n_ptr, max_pairs, key_bits, temp, st, sorted_in_b, launches, first_pass);
+  return radix_sort_pairs_t<RS_THREADS>(keys_a, vals_a, keys_b, vals_b, n_ptr, max_pairs, key_bits, temp, st, sorted_in_b, launches, first_pass);
 }
 
 }  // namespace mira_host
