@@ -256,8 +256,11 @@ class CommitmentKey:
         on their H2D slices unless `slices` == 1; device-resident commits only when `slices` >= 2 (default 0: whole)."""
         _check(N.lib().mira_msm_set_pipeline(self._ctx, slices, min_scalars_per_slice))
 
+    AFFINE_THREAD_LOCAL_PAIRS = -2
+
     def set_affine_levels(self, levels: int):
-        """Experimental (default 0): batched-affine pre-reduction levels before the XYZZ accumulation."""
+        """Experimental (default 0): batched-affine pre-reduction levels before the XYZZ accumulation;
+        AFFINE_THREAD_LOCAL_PAIRS (-2) = the thread-local pair pre-addition of round 2 (measured slower)."""
         _check(N.lib().mira_msm_set_affine_levels(self._ctx, levels))
 
     def close(self):

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "field_gen.cuh"
+#include "inv30.cuh"
 
 // Multiplier: the interleaved word-serial product of field_gen.cuh (128 wide MACs + 8 IMAD per product), with
 // MIRA_DUAL_MUL a*b +- c*d as ONE interleaved pass under one reduction (192 wide MACs instead of 256).
@@ -258,48 +259,30 @@ template <class F> __device__ __noinline__ Fe<F> fe_inv(const Fe<F>& a) {
   return fe_mul(fe_mul(r, r2), r2);
 }
 
-// The same inverse by a branch-uniform binary GCD, for code where all 32 lanes of a warp invert at once (fe_inv's
-// data-dependent inner loops would then serialise).  Loop: u even -> halve; u odd -> (swap so that u >= v), u -= v,
-// halve; v stays odd, and u = 0 leaves v = gcd = 1 with x2 = A^{-1}.  Every step is selects and carry chains.
+// The same inverse for code where all 32 lanes of a warp invert at once (fe_inv's data-dependent inner loops would
+// serialise there): batched division steps on 30-bit limbs (inv30.cuh), branch-free, ~14,000 instructions per
+// inversion.  Round 1's version of this function was a branch-uniform bit-by-bit binary GCD on four 256-bit numbers
+// (~115,000 executed instructions per inversion, ncu); it is what made a per-thread inversion unaffordable inside
+// the accumulation kernel.
+template <class F> struct Inv30Mod {
+  __host__ __device__ static constexpr uint32_t word(int i) { return FieldParams<F>::mod(i); }
+  __host__ __device__ static constexpr int32_t limb(int i) {
+    const int bit = 30 * i, k = bit >> 5, sh = bit & 31;
+    const uint64_t lo = FieldParams<F>::mod(k), hi = k + 1 < 8 ? FieldParams<F>::mod(k + 1) : 0u;
+    return (int32_t)((((hi << 32) | lo) >> sh) & 0x3fffffffu);
+  }
+  __host__ __device__ static constexpr uint32_t minv30() {       // 1 / M mod 2^30 by Newton's iteration
+    const uint32_t m0 = FieldParams<F>::mod(0);
+    uint32_t x = m0;
+    for (int i = 0; i < 5; i++) x *= 2u - m0 * x;
+    return x & 0x3fffffffu;
+  }
+};
 template <class F> __device__ __noinline__ Fe<F> fe_inv_uniform(const Fe<F>& a) {
-  if (fe_is_zero(a)) return a;
-  uint32_t u[8], v[8], x1[8], x2[8], p[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    u[i] = a.v[i];
-    p[i] = v[i] = FieldParams<F>::mod(i);
-    x1[i] = (i == 0);
-    x2[i] = 0;
-  }
-  for (;;) {
-    uint32_t nz = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) nz |= u[i];
-    if (!nz) break;
-    if (u[0] & 1u) {
-      if (!u256_ge(u, v)) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          uint32_t t = u[i]; u[i] = v[i]; v[i] = t;
-          t = x1[i]; x1[i] = x2[i]; x2[i] = t;
-        }
-      }
-      u256_sub(u, v);
-      if (u256_sub(x1, x2)) u256_add(x1, p);
-    }
-    u256_shr1(u);
-    if (x1[0] & 1u) {
-      // (x1 + p) / 2 without losing the carry out of bit 255: p < 2^254, so x1 + p < 2^255 fits
-      u256_add(x1, p);
-    }
-    u256_shr1(x1);
-  }
   Fe<F> r, r2;
+  inv30::modinv<Inv30Mod<F>>(r.v, a.v);          // (a R)^-1 = a^-1 R^-1 as a plain residue; 0 -> 0
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r.v[i] = x2[i];
-    r2.v[i] = FieldParams<F>::r2(i);
-  }
+  for (int i = 0; i < 8; i++) r2.v[i] = FieldParams<F>::r2(i);
   return fe_mul(fe_mul(r, r2), r2);
 }
 

@@ -494,7 +494,8 @@ int mira_msm_set_affine_levels(mira_msm_ctx* ctx, int levels) {
   if (!ctx) return fail(MIRA_ERR_INVALID, "null context");
   { int frc; if (for_each_shard(ctx, &frc, [&](mira_msm_ctx* sub) { return mira_msm_set_affine_levels(sub, levels); })) return frc; }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (levels < 0 || levels > 6) return fail(MIRA_ERR_INVALID, "affine levels %d out of range [0, 6]", levels);
+  if (levels != MIRA_AFFINE_THREAD_LOCAL_PAIRS && (levels < 0 || levels > 6))
+    return fail(MIRA_ERR_INVALID, "affine levels %d out of range [0, 6] (or MIRA_AFFINE_THREAD_LOCAL_PAIRS)", levels);
   ctx->affine_levels = levels;
   return MIRA_OK;
 }

@@ -358,6 +358,205 @@ __global__ void __launch_bounds__(128, MIRA_ACC_MIN_BLOCKS) k_accumulate(const u
   part_keys[2 * t + 1] = pk1;
 }
 
+// ------------------------------------------------------------------ accumulate with thread-local pair pre-addition
+// The same chunked walk as k_accumulate, but entries 2k and 2k+1 of a chunk, when they belong to the same bucket,
+// are first added in AFFINE coordinates and only their sum goes through the XYZZ mixed addition: 6 field products
+// (5M + 1S, Montgomery's trick included) + one 10-product mixed addition per TWO table points instead of two mixed
+// additions, i.e. ~2,090 wide MACs against ~2,540.  The batch that shares an inversion is the thread's own chunk
+// (~120 additions): no inter-thread exchange; every lane inverts its own product with the branch-free safegcd of
+// inv30.cuh (~14,000 instructions).  Three launches over the same chunking (thread t owns entries [t*L, (t+1)*L)):
+//   k_pair_up    descending: suffix[k] = prod_{j > k} d_j over the chunk's pairable pairs, d_k = x(2k+1) - x(2k),
+//                to a [pair][thread] scratch array (32 B, coalesced); then inv[t] = 1 / prod_j d_j.  Gathers the
+//                x-coordinates only; memory-latency-bound, many warps per SM.
+//   k_pair_add   ascending: 1/d_k = inv * suffix[k], inv *= d_k; lambda = (y2 - y1)/d_k; the sum goes to sums[k]
+//                ([pair][thread], 64 B); (0, 0) marks "not paired" (a sum is never the identity: opposite points
+//                are not pairable).  Integer-multiply-bound, five products per pair.
+//   k_pair_acc   k_accumulate's run bookkeeping over the sums (or, where not paired, the two table points).
+// One fused kernel was measured first (profiles/r02_pair_preadd.txt): with its three loops and the inversion in one
+// instruction stream (80 KB) and the warps of an SM in different loops, 22 % of all stall samples were instruction
+// fetch, and the latency-bound up pass (25 % of the samples) ran at 3 warps per scheduler.
+// A pair is skipped (both points take the mixed addition, which handles every exceptional case) when the keys
+// differ, when d_k = 0 (equal or opposite points) or when an x-coordinate is 0 (the identity is stored as (0, 0)).
+template <class CF>
+__device__ __forceinline__ Fe<CF> load_ref_x(const void* __restrict__ table, uint32_t ref) {
+  return fe_load<CF>(reinterpret_cast<const char*>(table) + (size_t)(ref & ~REF_NEG) * 64);
+}
+template <class CF>
+__device__ __forceinline__ bool pa_pairable(const Fe<CF>& x1, const Fe<CF>& x2, const Fe<CF>& d) {
+  return !fe_is_zero(d) && !fe_is_zero(x1) && !fe_is_zero(x2);
+}
+constexpr int PAIR_UP_AHEAD = 4;       // pairs whose x-coordinates are in flight while one product is computed
+
+template <class CF>
+__global__ void __launch_bounds__(128) k_pair_up(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ srefs,
+                                                 const uint32_t* __restrict__ n_ptr, int L, const void* __restrict__ table,
+                                                 void* __restrict__ suffix, void* __restrict__ inv_out) {
+  const uint32_t n_sorted = *n_ptr;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nth = (size_t)gridDim.x * blockDim.x;
+  const size_t begin = (size_t)t * L;
+  if (begin >= n_sorted) return;
+  const size_t end = begin + L < n_sorted ? begin + L : n_sorted;
+  const int m = (int)((end - begin + 1) >> 1);                 // pairs (the last one may hold a single entry)
+  char* const my_suffix = reinterpret_cast<char*>(suffix) + (size_t)t * 32;
+  Fe<CF> r = fe_one<CF>();
+  // ring of PAIR_UP_AHEAD pairs: the gathers of pairs k-1 .. k-AHEAD are in flight during pair k's product
+  Fe<CF> x1[PAIR_UP_AHEAD], x2[PAIR_UP_AHEAD];
+  bool same[PAIR_UP_AHEAD];
+#pragma unroll
+  for (int a = 0; a < PAIR_UP_AHEAD; a++) {
+    const int k = m - 1 - a;
+    same[a] = false;
+    x1[a] = fe_zero<CF>();
+    x2[a] = fe_zero<CF>();
+    if (k >= 0) {
+      const size_t e = begin + 2 * (size_t)k;
+      if (e + 1 < end && skeys[e] == skeys[e + 1]) {
+        same[a] = true;
+        x1[a] = load_ref_x<CF>(table, srefs[e]);
+        x2[a] = load_ref_x<CF>(table, srefs[e + 1]);
+      }
+    }
+  }
+  for (int k0 = m - 1; k0 >= 0; k0 -= PAIR_UP_AHEAD) {
+#pragma unroll
+    for (int a = 0; a < PAIR_UP_AHEAD; a++) {
+      const int k = k0 - a;
+      if (k < 0) break;
+      const Fe<CF> cx1 = x1[a], cx2 = x2[a];
+      const bool csame = same[a];
+      {                                                         // refill slot a with pair k - AHEAD
+        const int kn = k - PAIR_UP_AHEAD;
+        same[a] = false;
+        if (kn >= 0) {
+          const size_t e = begin + 2 * (size_t)kn;
+          if (skeys[e] == skeys[e + 1]) {
+            same[a] = true;
+            x1[a] = load_ref_x<CF>(table, srefs[e]);
+            x2[a] = load_ref_x<CF>(table, srefs[e + 1]);
+          }
+        }
+      }
+      if (csame) {
+        Fe<CF> d = fe_sub(cx2, cx1);
+        if (pa_pairable(cx1, cx2, d)) {
+          fe_store<CF>(my_suffix + (size_t)k * nth * 32, r);
+          r = fe_mul(r, d);
+        }
+      }
+    }
+  }
+  fe_store<CF>(reinterpret_cast<char*>(inv_out) + (size_t)t * 32, fe_inv_uniform(r));
+}
+
+template <class CF>
+__global__ void __launch_bounds__(128) k_pair_add(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ srefs,
+                                                  const uint32_t* __restrict__ n_ptr, int L, const void* __restrict__ table,
+                                                  const void* __restrict__ suffix, const void* __restrict__ inv_in,
+                                                  void* __restrict__ sums) {
+  const uint32_t n_sorted = *n_ptr;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nth = (size_t)gridDim.x * blockDim.x;
+  const size_t begin = (size_t)t * L;
+  if (begin >= n_sorted) return;
+  const size_t end = begin + L < n_sorted ? begin + L : n_sorted;
+  const int m = (int)((end - begin + 1) >> 1);
+  const char* const my_suffix = reinterpret_cast<const char*>(suffix) + (size_t)t * 32;
+  char* const my_sums = reinterpret_cast<char*>(sums) + (size_t)t * 64;
+  Fe<CF> inv = fe_load_plain<CF>(reinterpret_cast<const char*>(inv_in) + (size_t)t * 32);
+  for (int k = 0; k < m; k++) {
+    const size_t e = begin + 2 * (size_t)k;
+    const bool have_q = e + 1 < end;
+    Affine<CF> S;
+    S.x = fe_zero<CF>();
+    S.y = fe_zero<CF>();
+    if (have_q && skeys[e] == skeys[e + 1]) {
+      if (e + 5 < end) {                                        // pull the points two pairs ahead into L2
+        const char* n0 = reinterpret_cast<const char*>(table) + (size_t)(srefs[e + 4] & ~REF_NEG) * 64;
+        const char* n1 = reinterpret_cast<const char*>(table) + (size_t)(srefs[e + 5] & ~REF_NEG) * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(n0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(n1));
+      }
+      const Affine<CF> P = load_ref<CF>(table, srefs[e]);
+      const Affine<CF> Q = load_ref<CF>(table, srefs[e + 1]);
+      Fe<CF> d = fe_sub(Q.x, P.x);
+      if (pa_pairable(P.x, Q.x, d)) {
+        Fe<CF> sfx = fe_load<CF>(my_suffix + (size_t)k * nth * 32);
+        Fe<CF> ik = fe_mul(inv, sfx);                           // 1 / d
+        inv = fe_mul(inv, d);
+        Fe<CF> lam = fe_mul(fe_sub(Q.y, P.y), ik);
+        S.x = fe_sub(fe_sub(fe_sqr(lam), P.x), Q.x);
+        S.y = fe_sub(fe_mul(lam, fe_sub(P.x, S.x)), P.y);
+      }
+    }
+    aff_store<CF>(my_sums + (size_t)k * nth * 64, S);
+  }
+}
+
+template <class CF>
+__global__ void __launch_bounds__(128, MIRA_ACC_MIN_BLOCKS) k_pair_acc(const uint32_t* __restrict__ skeys,
+                                                  const uint32_t* __restrict__ srefs,
+                                                  const uint32_t* __restrict__ n_ptr, int L,
+                                                  const void* __restrict__ table, void* __restrict__ buckets,
+                                                  uint32_t* __restrict__ part_keys, void* __restrict__ part_pts, int add_mode,
+                                                  const void* __restrict__ sums) {
+  const uint32_t n_sorted = *n_ptr;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nth = (size_t)gridDim.x * blockDim.x;
+  const size_t begin = (size_t)t * L;
+  if (begin >= n_sorted) return;
+  const size_t end = begin + L < n_sorted ? begin + L : n_sorted;
+  const char* const my_sums = reinterpret_cast<const char*>(sums) + (size_t)t * 64;
+  const uint32_t prev_key = begin ? skeys[begin - 1] : 0u;
+  const uint32_t next_key = end < n_sorted ? skeys[end] : 0u;
+  uint32_t cur = skeys[begin];
+  bool first = true;
+  uint32_t pk0 = 0, pk1 = 0;
+  Xyzz<CF> acc = xyzz_identity<CF>();
+  if (add_mode && prev_key != cur) acc = xyzz_load_shared<CF>(reinterpret_cast<const char*>(buckets) + (size_t)cur * 128);
+  for (size_t e = begin; e < end;) {                            // ONE copy of the mixed addition in the instruction stream
+    const uint32_t key = skeys[e];
+    const uint32_t off = (uint32_t)(e - begin);
+    Affine<CF> P;
+    P.x = fe_zero<CF>();
+    P.y = fe_zero<CF>();
+    if (!(off & 1u)) P = aff_load<CF>(my_sums + (size_t)(off >> 1) * nth * 64);
+    if (aff_is_identity(P)) {                                   // rare: run edges, equal / opposite / identity points
+      P = load_ref<CF>(table, srefs[e]);
+      e += 1;
+    } else {
+      e += 2;
+    }
+    if (key != cur) {
+      if (first && prev_key == cur) {
+        pk0 = cur | PK_OPEN_LEFT;
+        xyzz_store<CF>(reinterpret_cast<char*>(part_pts) + (size_t)(2 * t) * 128, acc);
+      } else {
+        xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)cur * 128, acc);
+      }
+      first = false;
+      cur = key;
+      if (add_mode) acc = xyzz_load_shared<CF>(reinterpret_cast<const char*>(buckets) + (size_t)cur * 128);
+      else acc = xyzz_identity<CF>();
+    }
+    xyzz_madd(acc, P);
+  }
+  {
+    bool open_left = first && prev_key == cur;
+    bool open_right = next_key == cur;
+    if (!open_left && !open_right) {
+      xyzz_store<CF>(reinterpret_cast<char*>(buckets) + (size_t)cur * 128, acc);
+    } else {
+      uint32_t pk = cur | (open_left ? PK_OPEN_LEFT : 0u) | (open_right ? PK_OPEN_RIGHT : 0u);
+      int slot = first ? 0 : 1;
+      if (slot == 0) pk0 = pk; else pk1 = pk;
+      xyzz_store<CF>(reinterpret_cast<char*>(part_pts) + (size_t)(2 * t + slot) * 128, acc);
+    }
+  }
+  part_keys[2 * t] = pk0;
+  part_keys[2 * t + 1] = pk1;
+}
+
 // One thread per partial slot; the leftmost piece of each straddling run (not OPEN_LEFT) walks right
 // over slot 0 of the following chunks while the run stays open, and writes the bucket.  A run that
 // spans more than HEAVY_CHUNKS chunks (a "heavy" bucket: witness-like scalars put a large share of all

@@ -467,7 +467,40 @@ int msm_acc(mira_msm_ctx* ctx, MsmPlan* plan, bool add_mode, int bs, cudaStream_
         cudaFuncSetAttribute(k_accumulate<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
       });
     }
-    if (acc_direct)
+    // Thread-local pair pre-addition (k_pair_up / k_pair_add / k_pair_acc, msm_kernels.cuh): OFF by default — measured
+    // slower than the plain kernel on B200 (2^24 points: 6.1 + 13.8 + 16.3 = 36.2 ms against 31.8 ms; the two extra
+    // gathers of every table point cost 134 B of DRAM traffic each and make the first two kernels memory-bound,
+    // profiles/r02_pair_preadd.txt).  mira_msm_set_affine_levels(ctx, MIRA_AFFINE_THREAD_LOCAL_PAIRS) turns it on for
+    // a context (any chunk length: what the parity tests use), MIRA_ACC_PAIR=1 for a process (chunks of >= 128 pairs,
+    // MIRA_ACC_PAIR_MIN_L moves that).
+    static const int pair_env = [] { const char* e = getenv("MIRA_ACC_PAIR"); return e ? atoi(e) : 0; }();
+    static const int pair_env_min_l = [] { const char* e = getenv("MIRA_ACC_PAIR_MIN_L"); return e ? atoi(e) : 128; }();
+    const bool pair_ctx = ctx->affine_levels == MIRA_AFFINE_THREAD_LOCAL_PAIRS;
+    const bool pair_on = pair_ctx || (pair_env && ctx->affine_levels < 0);
+    const int pair_min_l = pair_ctx ? 2 : pair_env_min_l;
+    const unsigned acc_blocks = (n_chunks + 127) / 128;
+    bool use_pair = pair_on && !acc_direct && L >= pair_min_l && pad_kb <= 0;
+    if (use_pair) {
+      const size_t pa_threads = (size_t)acc_blocks * 128, pa_slots = (size_t)((L + 1) / 2) * pa_threads;     // [pair][thread]
+      const size_t need = pa_slots * (32 + 64) + pa_threads * 32 + 512;       // suffix products | sums | per-thread inverses
+      if (need > ctx->pa_work.cap) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need + ((size_t)2 << 30) > free_b + ctx->pa_work.cap) use_pair = false;
+      }
+      if (use_pair && (rc = ctx->pa_work.ensure(need))) return rc;
+    }
+    if (use_pair) {
+      const size_t pa_threads = (size_t)acc_blocks * 128, pa_slots = (size_t)((L + 1) / 2) * pa_threads;
+      char* sfx = (char*)ctx->pa_work.p;
+      char* sums = sfx + ((pa_slots * 32 + 255) & ~(size_t)255);
+      char* invs = sums + ((pa_slots * 64 + 255) & ~(size_t)255);
+      k_pair_up<CF><<<acc_blocks, 128, 0, st>>>(acc_keys, acc_refs, acc_n, L, acc_points, sfx, invs);
+      k_pair_add<CF><<<acc_blocks, 128, 0, st>>>(acc_keys, acc_refs, acc_n, L, acc_points, sfx, invs, sums);
+      k_pair_acc<CF><<<acc_blocks, 128, 0, st>>>(acc_keys, acc_refs, acc_n, L, acc_points, ctx->buckets.p, (uint32_t*)ctx->part_keys.p,
+                                                ctx->part_pts.p, add_mode ? 1 : 0, sums);
+      plan->launches += 2;
+    }
+    else if (acc_direct)
       k_accumulate<CF, true><<<(n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, nullptr, acc_n, L, acc_points, ctx->buckets.p,
                                                                     (uint32_t*)ctx->part_keys.p, ctx->part_pts.p, add_mode ? 1 : 0);
     else

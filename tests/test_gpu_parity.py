@@ -132,7 +132,7 @@ def test_commit_edge_cases(gpu, curve):
         vals[i] = 1 << 200                                             # only one high window set
     sc = b"".join(R.to_mont_bytes(v, sm) for v in vals)
     ck = CommitmentKey(curve, bases)
-    for c, levels in ((0, 0), (4, 0), (11, 0), (4, 3), (11, 6), (2, 2)):
+    for c, levels in ((0, 0), (4, 0), (11, 0), (4, 3), (11, 6), (2, 2), (0, -2), (4, -2), (11, -2)):     # -2: thread-local pairs
         ck.set_window(c)
         ck.set_affine_levels(levels)      # the batched-affine levels meet the same duplicates / negations / identities
         assert ck.commit(sc) == O.commit(curve, bases, sc)
@@ -426,7 +426,7 @@ def test_batched_affine_levels_only_change_speed(gpu, curve):
         sc[32 * 11:32 * 12] = sc[32 * 10:32 * 11]                  # s*P + s*(-P): cancellation inside a bucket
         vectors.append(bytes(sc))
     want = [O.commit(curve, bases, v) for v in vectors]
-    for levels in (0, 1, 3, 6):
+    for levels in (0, 1, 3, 6, CommitmentKey.AFFINE_THREAD_LOCAL_PAIRS):
         ck.set_affine_levels(levels)
         for c in (0, 9):
             ck.set_window(c)
