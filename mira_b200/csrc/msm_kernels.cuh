@@ -128,9 +128,17 @@ __global__ void __launch_bounds__(DG_THREADS) k_digits(const void* __restrict__ 
 // At 2^24 points: digits 0.71 + first pass 1.64 ms -> see DESIGN.md section 6.  Block-to-block order inside a bin
 // depends on the atomics' arrival order; the commitment does not (group addition is commutative and the result is
 // normalised), and the later passes are stable.
+// Block geometry, measured at 2^24 points (digit phase, ms): 512 scalars / 6144 pairs 1.375 | 384 / 4608 1.370 |
+// 256 / 3072 1.329 (profiles/r02_fused_digits.txt)
+#ifndef MIRA_DS_CAP
+#define MIRA_DS_CAP 3072
+#endif
+#ifndef MIRA_DS_SPB_MAX
+#define MIRA_DS_SPB_MAX 256
+#endif
 constexpr int DS_THREADS = 256;
-constexpr int DS_CAP = 6144;               // pairs staged per block (48 KiB of keys + refs)
-constexpr int DS_SPB_MAX = 512;            // scalars per block
+constexpr int DS_CAP = MIRA_DS_CAP;        // pairs staged per block (24 KiB of keys + refs)
+constexpr int DS_SPB_MAX = MIRA_DS_SPB_MAX;   // scalars per block
 
 __host__ __device__ inline uint32_t ds_scalars_per_block(int W) {
   uint32_t spb = (uint32_t)DS_CAP / (uint32_t)W;
