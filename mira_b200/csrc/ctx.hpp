@@ -89,7 +89,9 @@ struct mira_msm_ctx {
   int forced_window = 0;
   bool adaptive_window = true;                 // pick the window from a sample of the scalars (sparse witnesses want a narrow one)
   mira_host::DevBuf sample;                    // sampled scalars + bit-length histogram
-  uint32_t* h_hist = nullptr;                  // pinned, 260 u32 (257 histogram bins; word 258: pair count read back for sparse vectors)
+  uint32_t* h_hist = nullptr;                  // pinned, 2048 u32 (257 bit-length bins; word 258: pair count read back for sparse vectors;
+                                               // 260..1283: hash counts of the sampled scalars)
+  bool sampled_heavy = false;                  // the sample of the CURRENT commit holds a value that makes up > ~1.5 % of the vector
   double sampled_pairs_per_scalar = 0.0;       // density the sample of the CURRENT commit predicts (0 = not sampled)
   size_t slice_min = (size_t)1 << 19;          // host-buffer commits: smallest (first) slice of the geometric H2D pipeline
   bool profiling = false;

@@ -189,7 +189,7 @@ int mira_msm_ctx_create(int curve, const void* bases, size_t n_bases, int bases_
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bases, n_bases ? n_bases * 64 : 64);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_result, 4096);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_hist, 260 * 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_hist, 2048 * 4);
   if (e == cudaSuccess && n_bases)
     e = cudaMemcpyAsync(ctx->d_bases, bases, n_bases * 64, bases_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

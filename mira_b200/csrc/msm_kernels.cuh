@@ -148,7 +148,7 @@ __host__ __device__ inline uint32_t ds_scalars_per_block(int W) {
 
 template <class SF>
 __global__ void __launch_bounds__(DS_THREADS) k_digit_hist(const void* __restrict__ scalars, uint32_t n, int c, int W, uint32_t key_offset,
-                                                           uint32_t* __restrict__ g_hist) {
+                                                           int bin_shift, uint32_t bin_bias, uint32_t* __restrict__ g_hist) {
   __shared__ uint32_t sh[256];
   __shared__ uint32_t sm_sc[DS_THREADS * 9];
   sh[threadIdx.x] = 0;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_digit_hist(const void* __restric
     uint32_t carry = 0, neg;
     for (int j = 0; j < W; j++) {
       uint32_t d = signed_digit(sc, j, c, carry, neg);
-      if (d) atomicAdd(&sh[(key_offset + d) & 0xffu], 1u);
+      if (d) atomicAdd(&sh[((key_offset + d - bin_bias) >> bin_shift) & 0xffu], 1u);
     }
   }
   __syncthreads();
@@ -202,9 +202,11 @@ static __global__ void __launch_bounds__(DS_THREADS) k_digit_scan(const uint32_t
 
 template <class SF>
 __global__ void __launch_bounds__(DS_THREADS) k_digits_scatter(const void* __restrict__ scalars, uint32_t n, uint32_t first, int c, int W,
-                                                               uint32_t n_cover, uint32_t key_offset, uint32_t spb,
+                                                               uint32_t n_cover, uint32_t key_offset, uint32_t spb, int bin_shift, uint32_t bin_bias,
                                                                uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ out_keys,
                                                                uint32_t* __restrict__ out_refs) {
+  // bin = ((key - bin_bias) >> bin_shift) & 255: shift 0, bias 0 for the LSD sort's first pass; the TOP byte of key - 1
+  // (keys start at 1, so key - 1 fills its bit range evenly) for the MSD partition below
   extern __shared__ uint32_t ds_dyn[];
   uint32_t* sc_all = ds_dyn;                       // [spb][9] canonical limbs
   uint32_t* st_keys = ds_dyn + spb * 9;            // [spb * W] pairs grouped by bin
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_digits_scatter(const void* __res
     uint32_t carry = 0, neg;
     for (int j = 0; j < W; j++) {
       uint32_t d = signed_digit(sc_all + s * 9, j, c, carry, neg);
-      if (d) atomicAdd(&cnt[(key_offset + d) & 0xffu], 1u);
+      if (d) atomicAdd(&cnt[((key_offset + d - bin_bias) >> bin_shift) & 0xffu], 1u);
     }
   }
   __syncthreads();
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_digits_scatter(const void* __res
       uint32_t d = signed_digit(sc_all + s * 9, j, c, carry, neg);
       if (d) {
         const uint32_t key = key_offset + d;
-        const uint32_t q = atomicAdd(&cnt[key & 0xffu], 1u);
+        const uint32_t q = atomicAdd(&cnt[((key - bin_bias) >> bin_shift) & 0xffu], 1u);
         st_keys[q] = key;
         st_refs[q] = ((uint32_t)j * n_cover + first + base_i + s) | neg;     // `scalars` is the slice starting at key index `first`
       }
@@ -249,19 +251,285 @@ __global__ void __launch_bounds__(DS_THREADS) k_digits_scatter(const void* __res
   __syncthreads();
   for (uint32_t q = threadIdx.x; q < total; q += DS_THREADS) {
     const uint32_t key = st_keys[q];
-    const uint32_t b = key & 0xffu;
+    const uint32_t b = ((key - bin_bias) >> bin_shift) & 0xffu;
     const uint32_t dst = gbase[b] + (q - dstart[b]);
     out_keys[dst] = key;
     out_refs[dst] = st_refs[q];
   }
 }
 
+// ---- MSD partition: grouping by key without a stable pass (round 2) ----------------------------------------------
+// k_accumulate needs equal keys to be contiguous (and ascending), nothing more, and a most-significant-digit-first
+// partition needs no stability anywhere: once the pairs are grouped by the key's top bits, every group is partitioned
+// on its own.  Everything below works on key - 1 (keys start at 1: bucket b of set s is s * (B + 1) + b, b >= 1), whose K
+// bits are evenly filled; with K in [17, 24]:
+//   k_digit_hist     (above, bin_shift = K - 8) histogram of the pairs' TOP key byte;
+//   k_msd_scan1      segment offsets, cursors, the tile table of the 256 top-byte segments, *n_out;
+//   k_digits_scatter (above, bin_shift = K - 8) the digit kernel scatters its pairs into the 256 segments;
+//   k_msd_hist16     tiles of a segment: histogram of the next 8 bits -> 65,536 group counts; k_msd_scan16 scans them;
+//   k_msd_mid        tiles of a segment: rank by the next 8 bits with shared-memory atomics, one global atomicAdd per
+//                    (tile, sub-bin) on that group's cursor, the tile re-ordered in shared memory and written in runs;
+//   k_msd_low        a block per run of groups: 2^(K-16)-bin counting sort of each group in shared memory (groups
+//                    beyond its capacity, i.e. skewed vectors, through two passes over global memory).
+// Against the LSD sort's two stable passes (135 instructions per pair each: warp-ballot ranking; a histogram and three
+// scan kernels in front of each) the unstable passes rank with one shared-memory atomic per pair.
+constexpr int MSD_GROUP_BITS = 16;
+constexpr int MSD_GROUPS = 1 << MSD_GROUP_BITS;
+constexpr int MSD_TILE = 4096;             // pairs per k_msd_hist16 / k_msd_mid block
+constexpr int MSD_M_THREADS = 512;
+constexpr int MSD_S_THREADS = 1024;        // k_msd_scan16
+
+// hist1[256] -> offs1[257] (segment starts, offs1[256] = pair count), cursor1 (a copy k_digits_scatter advances),
+// tile_tab[b] = number of MSD_TILE tiles in segments < b (tile_tab[256] = all tiles), *n_out.  One block of 256 threads.
+static __global__ void __launch_bounds__(DS_THREADS) k_msd_scan1(const uint32_t* __restrict__ hist1, uint32_t* __restrict__ offs1,
+                                                                 uint32_t* __restrict__ cursor1, uint32_t* __restrict__ tile_tab,
+                                                                 uint32_t* __restrict__ n_out) {
+  __shared__ uint32_t tmp[8];
+  const uint32_t mine = hist1[threadIdx.x];
+  uint32_t total, tiles_total;
+  const uint32_t ex = ds_scan256(mine, tmp, total);
+  offs1[threadIdx.x] = ex;
+  cursor1[threadIdx.x] = ex;
+  const uint32_t tex = ds_scan256((mine + MSD_TILE - 1) / MSD_TILE, tmp, tiles_total);
+  tile_tab[threadIdx.x] = tex;
+  if (threadIdx.x == 0) {
+    offs1[256] = total;
+    tile_tab[256] = tiles_total;
+    *n_out = total;
+  }
+}
+
+// which segment and which slice [lo, hi) of the pair list does tile `blockIdx.x` cover?  (thread 0 fills the three words)
+__device__ __forceinline__ void msd_locate_tile(const uint32_t* __restrict__ offs1, const uint32_t* __restrict__ tile_tab, uint32_t* seg_lo_hi) {
+  uint32_t lo = 0, hi = 255;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if (tile_tab[mid] <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t seg_hi = offs1[lo + 1];
+  const uint32_t t_lo = offs1[lo] + (blockIdx.x - tile_tab[lo]) * MSD_TILE;
+  seg_lo_hi[0] = lo;
+  seg_lo_hi[1] = t_lo;
+  seg_lo_hi[2] = t_lo + MSD_TILE < seg_hi ? t_lo + MSD_TILE : seg_hi;
+}
+
+static __global__ void __launch_bounds__(MSD_M_THREADS) k_msd_hist16(const uint32_t* __restrict__ in_keys, const uint32_t* __restrict__ offs1,
+                                                                     const uint32_t* __restrict__ tile_tab, int low_bits,
+                                                                     uint32_t* __restrict__ hist16) {
+  __shared__ uint32_t cnt[256], where[3];
+  if (blockIdx.x >= tile_tab[256]) return;
+  if (threadIdx.x == 0) msd_locate_tile(offs1, tile_tab, where);
+  if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t seg = where[0], lo = where[1], hi = where[2];
+  constexpr int ITEMS = MSD_TILE / MSD_M_THREADS;
+  uint32_t key[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint32_t idx = lo + k * MSD_M_THREADS + threadIdx.x;
+    key[k] = idx < hi ? __ldg(in_keys + idx) : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint32_t idx = lo + k * MSD_M_THREADS + threadIdx.x;
+    if (idx < hi) atomicAdd(&cnt[((key[k] - 1u) >> low_bits) & 255u], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 256 && cnt[threadIdx.x]) atomicAdd(&hist16[(seg << 8) + threadIdx.x], cnt[threadIdx.x]);
+}
+
+// hist16[65536] -> offs16[65537], cursor16 (a copy k_msd_mid advances).  One block of 1024 threads, 64 groups each.
+static __global__ void __launch_bounds__(MSD_S_THREADS) k_msd_scan16(const uint32_t* __restrict__ hist16, uint32_t* __restrict__ offs16,
+                                                                     uint32_t* __restrict__ cursor16) {
+  __shared__ uint32_t warp_sums[32];
+  constexpr int PER = MSD_GROUPS / MSD_S_THREADS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint4* src = reinterpret_cast<const uint4*>(hist16 + threadIdx.x * PER);
+  uint32_t v[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER / 4; k++) {
+    const uint4 q = src[k];
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    sum += q.x + q.y + q.z + q.w;
+  }
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;                             // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = (warp ? warp_sums[warp - 1] : 0u) + x - sum;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const uint32_t g = threadIdx.x * PER + k;
+    offs16[g] = run;
+    cursor16[g] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == MSD_S_THREADS - 1) offs16[MSD_GROUPS] = run;
+}
+
+static __global__ void __launch_bounds__(MSD_M_THREADS) k_msd_mid(const uint32_t* __restrict__ in_keys, const uint32_t* __restrict__ in_refs,
+                                                                  const uint32_t* __restrict__ offs1, const uint32_t* __restrict__ tile_tab,
+                                                                  uint32_t* __restrict__ cursor16, int low_bits,
+                                                                  uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_refs) {
+  __shared__ uint32_t cnt[256], dstart[256], gbase[256], tmp[MSD_M_THREADS / 32], where[3];
+  __shared__ uint32_t st_keys[MSD_TILE], st_refs[MSD_TILE];       // the tile grouped by sub-bin, so that it leaves in runs
+  if (blockIdx.x >= tile_tab[256]) return;
+  if (threadIdx.x == 0) msd_locate_tile(offs1, tile_tab, where);
+  if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t seg = where[0], lo = where[1], hi = where[2];
+  constexpr int ITEMS = MSD_TILE / MSD_M_THREADS;
+  uint32_t key[ITEMS], ref[ITEMS], rank[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint32_t idx = lo + k * MSD_M_THREADS + threadIdx.x;
+    key[k] = idx < hi ? __ldg(in_keys + idx) : 0u;
+    ref[k] = idx < hi ? __ldg(in_refs + idx) : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint32_t idx = lo + k * MSD_M_THREADS + threadIdx.x;
+    if (idx < hi) rank[k] = atomicAdd(&cnt[((key[k] - 1u) >> low_bits) & 255u], 1u);
+  }
+  __syncthreads();
+  {                                                  // exclusive scan of the 256 counts (warps 0..7), global reservations
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t mine = threadIdx.x < 256 ? cnt[threadIdx.x] : 0u;
+    uint32_t x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) tmp[warp] = x;
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      uint32_t off = 0;
+      for (int w = 0; w < warp; w++) off += tmp[w];
+      dstart[threadIdx.x] = off + x - mine;
+      gbase[threadIdx.x] = mine ? atomicAdd(&cursor16[(seg << 8) + threadIdx.x], mine) : 0u;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint32_t idx = lo + k * MSD_M_THREADS + threadIdx.x;
+    if (idx < hi) {
+      const uint32_t q = dstart[((key[k] - 1u) >> low_bits) & 255u] + rank[k];
+      st_keys[q] = key[k];
+      st_refs[q] = ref[k];
+    }
+  }
+  __syncthreads();
+  const uint32_t count = hi - lo;
+  for (uint32_t q = threadIdx.x; q < count; q += MSD_M_THREADS) {
+    const uint32_t kk = st_keys[q];
+    const uint32_t sub = ((kk - 1u) >> low_bits) & 255u;
+    const uint32_t dst = gbase[sub] + (q - dstart[sub]);
+    out_keys[dst] = kk;
+    out_refs[dst] = st_refs[q];
+  }
+}
+
+// Block b sorts groups [b * gpb, (b + 1) * gpb) by the key's low `low_bits` (1..8) bits.  A range
+// of up to MSD_LOW_CAP pairs is ranked from registers, re-ordered in shared memory and written back in order (coalesced);
+// a larger one (skewed vectors) goes through two passes over global memory: histogram, then placement.
+constexpr int MSD_L_THREADS = 256;
+constexpr int MSD_LOW_ITEMS = 16;
+constexpr int MSD_LOW_CAP = MSD_L_THREADS * MSD_LOW_ITEMS;      // 4096 pairs, 32 KiB
+constexpr int MSD_LOW_MAX_AVG = 3400;                           // the host uses the MSD path while pairs / groups stays below this
+
+static __global__ void __launch_bounds__(MSD_L_THREADS) k_msd_low(const uint32_t* __restrict__ in_keys, const uint32_t* __restrict__ in_refs,
+                                                                  const uint32_t* __restrict__ offs16, uint32_t gpb, int low_bits,
+                                                                  uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_refs) {
+  __shared__ uint32_t cnt[256], tmp[8];
+  __shared__ uint32_t st_keys[MSD_LOW_CAP], st_refs[MSD_LOW_CAP];
+  // gpb (a power of two) adjacent groups are one contiguous range of pairs that share the top bits, so sorting the
+  // range by the low bits PLUS the log2(gpb) bits above them sorts every group in it: one pass per block whatever gpb is
+  // (the host keeps low_bits + log2(gpb) <= 8)
+  uint32_t span_bits = (uint32_t)low_bits;
+  for (uint32_t x = gpb; x > 1; x >>= 1) span_bits++;
+  const uint32_t mask = (1u << span_bits) - 1u;
+  {
+    const uint32_t g = blockIdx.x * gpb;
+    const uint32_t lo = offs16[g], hi = offs16[g + gpb];
+    if (lo == hi) return;                            // uniform per block: offs16 is read by every thread alike
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t total;
+    if (hi - lo <= (uint32_t)MSD_LOW_CAP) {
+      uint32_t key[MSD_LOW_ITEMS], ref[MSD_LOW_ITEMS], rank[MSD_LOW_ITEMS];
+#pragma unroll
+      for (int k = 0; k < MSD_LOW_ITEMS; k++) {
+        const uint32_t i = lo + k * MSD_L_THREADS + threadIdx.x;
+        key[k] = i < hi ? __ldg(in_keys + i) : 0u;
+        ref[k] = i < hi ? __ldg(in_refs + i) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < MSD_LOW_ITEMS; k++) {
+        const uint32_t i = lo + k * MSD_L_THREADS + threadIdx.x;
+        if (i < hi) rank[k] = atomicAdd(&cnt[(key[k] - 1u) & mask], 1u);
+      }
+      __syncthreads();
+      const uint32_t ex = ds_scan256(cnt[threadIdx.x], tmp, total);
+      cnt[threadIdx.x] = ex;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < MSD_LOW_ITEMS; k++) {
+        const uint32_t i = lo + k * MSD_L_THREADS + threadIdx.x;
+        if (i < hi) {
+          const uint32_t q = cnt[(key[k] - 1u) & mask] + rank[k];
+          st_keys[q] = key[k];
+          st_refs[q] = ref[k];
+        }
+      }
+      __syncthreads();
+      for (uint32_t q = threadIdx.x; q < hi - lo; q += MSD_L_THREADS) {
+        out_keys[lo + q] = st_keys[q];
+        out_refs[lo + q] = st_refs[q];
+      }
+      __syncthreads();
+    } else {
+      for (uint32_t i = lo + threadIdx.x; i < hi; i += MSD_L_THREADS) atomicAdd(&cnt[(__ldg(in_keys + i) - 1u) & mask], 1u);
+      __syncthreads();
+      const uint32_t ex = ds_scan256(cnt[threadIdx.x], tmp, total);
+      cnt[threadIdx.x] = lo + ex;                    // next free slot of every low value
+      __syncthreads();
+      for (uint32_t i = lo + threadIdx.x; i < hi; i += MSD_L_THREADS) {
+        const uint32_t k = __ldg(in_keys + i);
+        const uint32_t dst = atomicAdd(&cnt[(k - 1u) & mask], 1u);
+        out_keys[dst] = k;
+        out_refs[dst] = __ldg(in_refs + i);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Bit-length histogram of a SAMPLE of the scalars (n_chunks chunks of chunk_len consecutive scalars, `stride` apart):
 // hist[L] += 1 for every sampled scalar whose canonical value has bit length L (0 for zero).  Feeds
 // choose_window_sampled.  `src_stride` = distance between chunks in the source, in scalars.
+constexpr int SAMPLE_HASH_BINS = 1024;
 template <class SF>
 __global__ void __launch_bounds__(256) k_bitlen_hist(const void* __restrict__ scalars, uint32_t n_chunks, uint32_t chunk_len,
                                                      size_t src_stride, uint32_t* __restrict__ hist) {
+  // hist[0..256]: bit lengths; hist[260 .. 260 + SAMPLE_HASH_BINS): how many sampled scalars of bit length > 32 hash to
+  // each bin — a value that makes up more than a per cent or two of the vector stands out of the ~samples / bins
+  // background (heavy-hitter test for the MSD partition, pipeline.cuh)
   __shared__ uint32_t sh[257];
   for (int i = threadIdx.x; i < 257; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -274,6 +542,12 @@ __global__ void __launch_bounds__(256) k_bitlen_hist(const void* __restrict__ sc
     for (int k = 7; k >= 0; k--)
       if (L == 0 && s.v[k]) L = 32 * k + 32 - __clz(s.v[k]);
     atomicAdd(&sh[L], 1u);
+    if (L > 32) {
+      uint32_t h = s.v[0] * 0x9E3779B1u;
+#pragma unroll
+      for (int k = 1; k < 8; k++) h = (h ^ s.v[k]) * 0x85EBCA77u;
+      atomicAdd(&hist[260 + ((h >> 16) & (SAMPLE_HASH_BINS - 1))], 1u);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 257; i += blockDim.x)

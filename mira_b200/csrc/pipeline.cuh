@@ -141,12 +141,13 @@ int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device
   *window = 0;
   if (pairs_per_scalar) *pairs_per_scalar = 0.0;        // 0 = not sampled
   ctx->sampled_pairs_per_scalar = 0.0;
+  ctx->sampled_heavy = false;
   if (ctx->forced_window || !ctx->adaptive_window || n < ADAPT_MIN_N) return MIRA_OK;
   int rc;
   const size_t samples = (size_t)ADAPT_CHUNKS * ADAPT_CHUNK_LEN, stride = n / ADAPT_CHUNKS;
-  if ((rc = ctx->sample.ensure(samples * 32 + 260 * 4))) return rc;
+  if ((rc = ctx->sample.ensure(samples * 32 + (260 + SAMPLE_HASH_BINS) * 4))) return rc;
   uint32_t* d_hist = (uint32_t*)((char*)ctx->sample.p + samples * 32);
-  CU(cudaMemsetAsync(d_hist, 0, 260 * 4, st));
+  CU(cudaMemsetAsync(d_hist, 0, (260 + SAMPLE_HASH_BINS) * 4, st));
   const void* src = scalars;
   size_t src_stride = stride;
   if (!on_device) {
@@ -157,8 +158,13 @@ int pick_window(mira_msm_ctx* ctx, const void* scalars, size_t n, bool on_device
     src_stride = ADAPT_CHUNK_LEN;
   }
   k_bitlen_hist<SF><<<(unsigned)((samples + 255) / 256), 256, 0, st>>>(src, ADAPT_CHUNKS, ADAPT_CHUNK_LEN, src_stride, d_hist);
-  CU(cudaMemcpyAsync(ctx->h_hist, d_hist, 257 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_hist, d_hist, (260 + SAMPLE_HASH_BINS) * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  {                             // heavy hitters: a hash bin far above the samples / bins background (8 of 8192 per bin)
+    uint32_t mx = 0;
+    for (int b = 0; b < SAMPLE_HASH_BINS; b++) mx = std::max(mx, ctx->h_hist[260 + b]);
+    ctx->sampled_heavy = mx > samples / 64;              // one value in > 1/64 of the sampled scalars
+  }
   double costs[25];
   int best = choose_window_sampled(n, ctx->h_hist, samples, costs);
   // hysteresis: a table costs seconds and gigabytes to build, so a window that already has one covering n is kept
@@ -225,6 +231,7 @@ struct MsmPlan {
     size_t E_chunking = 0;          // pair count the accumulation's chunk length is chosen for
   } prep[2];
   int affine_levels = 0;
+  bool heavy = false;           // the sample found a heavy hitter: keep the LSD sort (the MSD partition's per-group pass would crawl)
   bool exact_count = false;     // sparse vector: read the pair count back after the digit kernel and size everything from it
   int c = 0, W = 0;
   Table* tab = nullptr;
@@ -254,7 +261,7 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
   for (int b = 0; b < n_bufsets; b++) {
     auto& sb = ctx->sb[b];
     if ((rc = sb.keys.ensure(E * 4 + 16)) || (rc = sb.refs.ensure(E * 4 + 16)) || (rc = sb.skeys.ensure(E * 4 + 16)) ||
-        (rc = sb.srefs.ensure(E * 4 + 16)) || (rc = sb.counts.ensure(4096)) || (rc = sb.tile_sums.ensure(radix_sort_temp_bytes(E))))
+        (rc = sb.srefs.ensure(E * 4 + 16)) || (rc = sb.counts.ensure((size_t)1 << 20)) || (rc = sb.tile_sums.ensure(radix_sort_temp_bytes(E))))
       return rc;
   }
   if ((rc = ctx->buckets.ensure(bucket_bytes))) return rc;
@@ -275,6 +282,8 @@ int msm_begin(mira_msm_ctx* ctx, size_t n, size_t max_slice, cudaStream_t st, Ms
   // digit kernel (the host synchronises once more, ~30 us) sizes the sort and the accumulation grid from the real count.
   static const int exact_on = [] { const char* e = getenv("MIRA_EXACT_COUNT"); return e ? atoi(e) : 1; }();
   plan->exact_count = exact_on && n_sets == 1 && ctx->sampled_pairs_per_scalar > 0.0 && ctx->sampled_pairs_per_scalar < 0.6 * W;
+  plan->heavy = ctx->sampled_heavy;
+  ctx->sampled_heavy = false;
   ctx->sampled_pairs_per_scalar = 0.0;          // belongs to the commit that sampled it (pick_window runs right before msm_begin)
   plan->launches = 0; plan->entries = 0;
   return MIRA_OK;
@@ -302,11 +311,40 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
   if (!add_mode) CU(cudaMemsetAsync((char*)sb.counts.p + 48, 0, 8, st));      // affine additions of this commit
   uint32_t* d_hist = (uint32_t*)((char*)sb.counts.p + 1024);                  // [256] low-byte histogram
   uint32_t* d_cursor = (uint32_t*)((char*)sb.counts.p + 2048);                // [256] next free slot of each bin
-  if (fused_on) {
+  // MSD partition instead of the LSD passes (msm_kernels.cuh): for 17..24 key bits, from MSD_MIN_PAIRS pairs (below that
+  // its fixed costs — 65,536 groups, two single-block scans — outweigh the cheaper ranking) and while an average group
+  // fits k_msd_low's shared-memory path (larger commits keep the LSD passes), and not when the sample of the vector shows
+  // a heavy hitter (a value repeated in > 1/64 of the scalars puts hundreds of thousands of pairs into W single
+  // buckets, and k_msd_low sorts a group with ONE block).  MIRA_SORT_MSD=0 keeps the LSD sort.
+  static const int msd_env = [] { const char* e = getenv("MIRA_SORT_MSD"); return e ? atoi(e) : 1; }();
+  static const size_t msd_min_pairs = [] { const char* e = getenv("MIRA_SORT_MSD_MIN_LOG"); return (size_t)1 << (e ? atoi(e) : 25); }();
+  int key_bits = c;          // keys are < n_sets * (B + 1)
+  while (((uint64_t)1 << key_bits) < (uint64_t)plan->n_sets * (plan->B + 1)) key_bits++;
+  int msd_bits = 1;          // the MSD partition works on key - 1 < n_sets * (B + 1) - 1 (a single set: c - 1 bits, evenly filled)
+  while (((uint64_t)1 << msd_bits) < (uint64_t)plan->n_sets * (plan->B + 1) - 1) msd_bits++;
+  const bool msd_on = fused_on && msd_env && !plan->heavy && msd_bits >= MSD_GROUP_BITS + 1 && msd_bits <= MSD_GROUP_BITS + 8 && E >= msd_min_pairs &&
+                      (E >> MSD_GROUP_BITS) <= (size_t)MSD_LOW_MAX_AVG;
+  const int low_bits = msd_bits - MSD_GROUP_BITS;
+  uint32_t* d_offs1 = (uint32_t*)((char*)sb.counts.p + 4096);                 // [257] segment starts
+  uint32_t* d_tile_tab = d_offs1 + 320;                                       // [257]
+  uint32_t* d_hist16 = (uint32_t*)((char*)sb.counts.p + 8192);                // [65536]
+  uint32_t* d_offs16 = d_hist16 + MSD_GROUPS;                                 // [65537] (+ padding)
+  uint32_t* d_cursor16 = d_offs16 + MSD_GROUPS + 64;                          // [65536]
+  if (msd_on) {
+    CU(cudaMemsetAsync(d_hist, 0, 1024, st));
+    CU(cudaMemsetAsync(d_hist16, 0, (size_t)MSD_GROUPS * 4, st));
+    const unsigned hist_blocks = (unsigned)std::min<size_t>((n + DS_THREADS - 1) / DS_THREADS, 148 * 8);
+    for (int s = 0; s < plan->n_sets; s++) {
+      k_digit_hist<SF><<<hist_blocks, DS_THREADS, 0, st>>>(d_scalar_sets[s], (uint32_t)n, c, W, (uint32_t)s * (plan->B + 1), msd_bits - 8, 1u, d_hist);
+      plan->launches++;
+    }
+    k_msd_scan1<<<1, DS_THREADS, 0, st>>>(d_hist, d_offs1, d_cursor, d_tile_tab, d_npairs);
+    plan->launches++;
+  } else if (fused_on) {
     CU(cudaMemsetAsync(d_hist, 0, 1024, st));
     const unsigned hist_blocks = (unsigned)std::min<size_t>((n + DS_THREADS - 1) / DS_THREADS, 148 * 8);
     for (int s = 0; s < plan->n_sets; s++) {
-      k_digit_hist<SF><<<hist_blocks, DS_THREADS, 0, st>>>(d_scalar_sets[s], (uint32_t)n, c, W, (uint32_t)s * (plan->B + 1), d_hist);
+      k_digit_hist<SF><<<hist_blocks, DS_THREADS, 0, st>>>(d_scalar_sets[s], (uint32_t)n, c, W, (uint32_t)s * (plan->B + 1), 0, 0u, d_hist);
       plan->launches++;
     }
     k_digit_scan<<<1, DS_THREADS, 0, st>>>(d_hist, d_cursor, d_npairs);
@@ -328,8 +366,6 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
     E_sort = *h_count ? *h_count : 1;               // an all-zero vector still launches (and finds nothing to do)
     if (E_sort > E) return fail(MIRA_ERR_CUDA, "pair count %zu exceeds its bound %zu", E_sort, E);
   }
-  int key_bits = c;          // keys are < n_sets * (B + 1)
-  while (((uint64_t)1 << key_bits) < (uint64_t)plan->n_sets * (plan->B + 1)) key_bits++;
   int in_b = 0;
   if (fused_on) {
     const uint32_t spb = ds_scalars_per_block(W);
@@ -338,21 +374,41 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     std::call_once(ds_once[dev_id & 63], [&] {
-      cudaFuncSetAttribute(k_digits_scatter<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SPB_MAX * 9 * 4 + DS_CAP * 8);
+      // the smallest block (32 scalars) of the narrowest window (c = 2: 128 digits per scalar) stages 4096 pairs
+      cudaFuncSetAttribute(k_digits_scatter<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           std::max(DS_SPB_MAX * 9 * 4 + DS_CAP * 8, 32 * 9 * 4 + 32 * 128 * 8));
     });
     for (int s = 0; s < plan->n_sets; s++) {
       k_digits_scatter<SF><<<(unsigned)((n + spb - 1) / spb), DS_THREADS, dyn, st>>>(
-          d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), spb, d_cursor,
-          (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p);
+          d_scalar_sets[s], (uint32_t)n, (uint32_t)first, c, W, tab->n_cover, (uint32_t)s * (plan->B + 1), spb, msd_on ? msd_bits - 8 : 0,
+          msd_on ? 1u : 0u, d_cursor, (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p);
       plan->launches++;
     }
     if (pt) pt->mark(1);
+    if (msd_on) {
+      // ---- MSD: group counts of the next 8 bits, the partition by them (s-buffers -> plain buffers), then every
+      // 16-bit group by its low bits (back into the s-buffers)
+      const unsigned tiles = (unsigned)(E_sort / MSD_TILE + 257);
+      k_msd_hist16<<<tiles, MSD_M_THREADS, 0, st>>>((const uint32_t*)sb.skeys.p, d_offs1, d_tile_tab, low_bits, d_hist16);
+      k_msd_scan16<<<1, MSD_S_THREADS, 0, st>>>(d_hist16, d_offs16, d_cursor16);
+      k_msd_mid<<<tiles, MSD_M_THREADS, 0, st>>>((const uint32_t*)sb.skeys.p, (const uint32_t*)sb.srefs.p, d_offs1, d_tile_tab, d_cursor16,
+                                                 low_bits, (uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p);
+      // groups per k_msd_low block: as many as keep the block's range around 3,000 pairs and its bins within 256
+      uint32_t gpb = 1;
+      for (int span = low_bits; span < 8 && (E_sort / MSD_GROUPS) * (gpb * 2) <= 3000; span++) gpb <<= 1;
+      k_msd_low<<<MSD_GROUPS / gpb, MSD_L_THREADS, 0, st>>>((const uint32_t*)sb.keys.p, (const uint32_t*)sb.refs.p, d_offs16, gpb, low_bits,
+                                                           (uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p);
+      plan->launches += 4;
+      CU(cudaGetLastError());
+      in_b = 1;
+    } else {
     // ---- the remaining passes (bit 8 up) of the LSD radix sort, from the s-buffers into the plain ones and back
     int in_plain = 0;
     if ((rc = radix_sort_pairs((uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, (uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, d_npairs, E_sort,
                                key_bits, sb.tile_sums.p, st, &in_plain, &plan->launches, 1)))
       return rc;
     in_b = !in_plain;
+    }
   } else {
     if (pt) pt->mark(1);
     // ---- group pairs by bucket: LSD radix sort on the c-bit key

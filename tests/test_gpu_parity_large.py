@@ -217,3 +217,28 @@ def test_very_sparse_long_vectors(gpu, curve):
         assert ck.commit_device(dev.data_ptr(), n) == want, name
         assert ck.commit(host) == want, name
     assert O.commit(curve, bases, cases[0][1].tobytes()) == bytes(64)
+
+
+def test_dense_vector_with_a_heavy_hitter_vs_oracle(gpu):
+    """A dense vector in which one full-length value is repeated in a quarter of the scalars (a column filled with -1,
+    say): every window then has ONE bucket holding a quarter of that window's pairs.  With the window chosen from the
+    sample the heavy hitter is detected and the LSD sort is kept; with a forced window there is no sample, so the MSD
+    partition runs and its per-group pass meets groups far beyond its shared-memory capacity.  Both must give the
+    oracle's bytes (2^22 points: enough pairs for the MSD path to be chosen)."""
+    from mira_b200 import CommitmentKey
+    import numpy as np
+    curve, n = R.BN254, 1 << 22
+    bases_dev = gpu.gen_bases_dev(curve, 0x48454156, n)
+    bases = gpu.to_bytes(bases_dev)
+    sc = gpu.gen_scalars_dev(curve, 0x48454157, n, 0)
+    host = np.frombuffer(bytearray(gpu.to_bytes(sc)), dtype=np.uint8).reshape(n, 32).copy()
+    rep = host[5].copy()                                            # a random full-length scalar
+    host[np.arange(0, n, 4)] = rep                                  # ... in every fourth position
+    host_sc = host.tobytes()
+    want = O.commit(curve, bases, host_sc)
+    d = torch.frombuffer(bytearray(host_sc), dtype=torch.uint8).cuda()
+    ck = CommitmentKey(curve, bases_dev, on_device=True)
+    assert ck.commit_device(d.data_ptr(), n) == want                # sampled: heavy hitter seen, LSD sort
+    ck.set_window(20)
+    assert ck.commit_device(d.data_ptr(), n) == want                # forced window: MSD partition, oversized groups
+    assert ck.commit(host_sc) == want
