@@ -275,8 +275,15 @@ __global__ void __launch_bounds__(DS_THREADS) k_digits_scatter(const void* __res
 // scan kernels in front of each) the unstable passes rank with one shared-memory atomic per pair.
 constexpr int MSD_GROUP_BITS = 16;
 constexpr int MSD_GROUPS = 1 << MSD_GROUP_BITS;
-constexpr int MSD_TILE = 4096;             // pairs per k_msd_hist16 / k_msd_mid block
-constexpr int MSD_M_THREADS = 512;
+#ifndef MIRA_MSD_TILE
+#define MIRA_MSD_TILE 4096
+#endif
+// k_msd_mid geometry, sort phase at 2^24 points (ms): 4096 pairs x 512 threads 2.001 | 2048 x 256 2.135 | 4096 x 256 1.956
+#ifndef MIRA_MSD_M_THREADS
+#define MIRA_MSD_M_THREADS 256
+#endif
+constexpr int MSD_TILE = MIRA_MSD_TILE;    // pairs per k_msd_hist16 / k_msd_mid block
+constexpr int MSD_M_THREADS = MIRA_MSD_M_THREADS;
 constexpr int MSD_S_THREADS = 1024;        // k_msd_scan16
 
 // hist1[256] -> offs1[257] (segment starts, offs1[256] = pair count), cursor1 (a copy k_digits_scatter advances),
@@ -338,27 +345,20 @@ static __global__ void __launch_bounds__(MSD_M_THREADS) k_msd_hist16(const uint3
   if (threadIdx.x < 256 && cnt[threadIdx.x]) atomicAdd(&hist16[(seg << 8) + threadIdx.x], cnt[threadIdx.x]);
 }
 
-// hist16[65536] -> offs16[65537], cursor16 (a copy k_msd_mid advances).  One block of 1024 threads, 64 groups each.
+// hist16[65536] -> offs16[65537], cursor16 (a copy k_msd_mid advances).  One block of 1024 threads: warp w owns the
+// 2048 consecutive groups [2048 w, 2048 (w + 1)) and walks them 32 at a time (coalesced loads and stores, warp scans).
 static __global__ void __launch_bounds__(MSD_S_THREADS) k_msd_scan16(const uint32_t* __restrict__ hist16, uint32_t* __restrict__ offs16,
                                                                      uint32_t* __restrict__ cursor16) {
   __shared__ uint32_t warp_sums[32];
-  constexpr int PER = MSD_GROUPS / MSD_S_THREADS;
+  constexpr int PER_WARP = MSD_GROUPS / (MSD_S_THREADS / 32);      // 2048
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint4* src = reinterpret_cast<const uint4*>(hist16 + threadIdx.x * PER);
-  uint32_t v[PER], sum = 0;
+  const uint32_t* src = hist16 + warp * PER_WARP;
+  uint32_t sum = 0;
+#pragma unroll 8
+  for (int i = 0; i < PER_WARP / 32; i++) sum += src[i * 32 + lane];
 #pragma unroll
-  for (int k = 0; k < PER / 4; k++) {
-    const uint4 q = src[k];
-    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-    sum += q.x + q.y + q.z + q.w;
-  }
-  uint32_t x = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) warp_sums[warp] = x;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) warp_sums[warp] = sum;
   __syncthreads();
   if (warp == 0) {
     uint32_t w = warp_sums[lane];
@@ -370,13 +370,20 @@ static __global__ void __launch_bounds__(MSD_S_THREADS) k_msd_scan16(const uint3
     warp_sums[lane] = w;                             // inclusive over warps
   }
   __syncthreads();
-  uint32_t run = (warp ? warp_sums[warp - 1] : 0u) + x - sum;
+  uint32_t run = warp ? warp_sums[warp - 1] : 0u;
+#pragma unroll 4
+  for (int i = 0; i < PER_WARP / 32; i++) {
+    const uint32_t v = src[i * 32 + lane];
+    uint32_t x = v;
 #pragma unroll
-  for (int k = 0; k < PER; k++) {
-    const uint32_t g = threadIdx.x * PER + k;
-    offs16[g] = run;
-    cursor16[g] = run;
-    run += v[k];
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    const uint32_t ex = run + x - v;
+    offs16[warp * PER_WARP + i * 32 + lane] = ex;
+    cursor16[warp * PER_WARP + i * 32 + lane] = ex;
+    run += __shfl_sync(0xffffffffu, x, 31);
   }
   if (threadIdx.x == MSD_S_THREADS - 1) offs16[MSD_GROUPS] = run;
 }
@@ -448,8 +455,11 @@ static __global__ void __launch_bounds__(MSD_M_THREADS) k_msd_mid(const uint32_t
 // Block b sorts groups [b * gpb, (b + 1) * gpb) by the key's low `low_bits` (1..8) bits.  A range
 // of up to MSD_LOW_CAP pairs is ranked from registers, re-ordered in shared memory and written back in order (coalesced);
 // a larger one (skewed vectors) goes through two passes over global memory: histogram, then placement.
+#ifndef MIRA_MSD_L_ITEMS
+#define MIRA_MSD_L_ITEMS 16
+#endif
 constexpr int MSD_L_THREADS = 256;
-constexpr int MSD_LOW_ITEMS = 16;
+constexpr int MSD_LOW_ITEMS = MIRA_MSD_L_ITEMS;
 constexpr int MSD_LOW_CAP = MSD_L_THREADS * MSD_LOW_ITEMS;      // 4096 pairs, 32 KiB
 constexpr int MSD_LOW_MAX_AVG = 3400;                           // the host uses the MSD path while pairs / groups stays below this
 
