@@ -557,3 +557,21 @@ def test_pipelined_commit_equals_unpipelined(gpu, curve):
         sc = O.gen_scalars(curve, 670 + m, m)
         d = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
         assert ck.commit_device(d.data_ptr(), m) == O.commit(curve, bases, sc), m
+
+
+def test_msd_partition_on_small_and_edge_inputs(gpu):
+    """The MSD partition (k_msd_* in msm_kernels.cuh) is used from 2^25 pairs on, so in this suite only the 2^22-point
+    tests reach it by size.  MIRA_SORT_MSD_MIN_LOG=0 (read once per process, hence the child process) removes the size
+    gate: the edge-case keys (identity / duplicate / negated generators, one repeated point), every window width from 17
+    bits up, the batched commit with its per-set bucket ranges, sliced host commits and the randomized sweep then all go
+    through it and must still give the oracle's bytes."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MIRA_SORT_MSD_MIN_LOG="0", MIRA_SWEEP_CONFIGS="24")
+    here = os.path.abspath(__file__)
+    sel = ["test_commit_edge_cases", "test_commit_all_window_widths", "test_batched_affine_levels_only_change_speed",
+           "test_randomized_commit_configurations"]
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", " or ".join(sel)],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(here)))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
