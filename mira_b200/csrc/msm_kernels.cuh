@@ -865,13 +865,17 @@ __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ sk
                                                  void* __restrict__ buckets, uint32_t* __restrict__ heavy,
                                                  uint32_t heavy_cap) {
   // heavy = [count_medium, count_huge, medium leaders (heavy_cap), huge leaders (heavy_cap)]
+  // One thread per CHUNK: a chunk has at most one piece that leads a straddling run (its last run if that continues
+  // into the next chunk — slot 1, or slot 0 when the whole chunk is one run that starts at its left edge); a thread
+  // per slot left every other lane idle.
   const uint32_t n = *n_ptr;
   const uint32_t n_chunks = (n + L - 1) / L;
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= 2 * n_chunks) return;
-  uint32_t pk = part_keys[q];
+  uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= n_chunks) return;
+  const uint2 pks = reinterpret_cast<const uint2*>(part_keys)[chunk];
+  uint32_t q = pks.y ? 2 * chunk + 1 : 2 * chunk;
+  uint32_t pk = pks.y ? pks.y : pks.x;
   if (pk == 0 || (pk & PK_OPEN_LEFT)) return;
-  uint32_t chunk = q >> 1;
   {
     uint64_t probe = (uint64_t)(chunk + HEAVY_CHUNKS) * (uint32_t)L;
     if (probe < n && skeys[probe] == (pk & PK_KEY_MASK)) {

@@ -566,7 +566,7 @@ int msm_acc(mira_msm_ctx* ctx, MsmPlan* plan, bool add_mode, int bs, cudaStream_
     if ((rc = ctx->cursor.ensure(((size_t)heavy_cap * 2 + 4) * 4))) return rc;
     uint32_t* d_heavy = (uint32_t*)ctx->cursor.p;     // [0], [1] = counts, then the medium and the huge leader lists
     CU(cudaMemsetAsync(d_heavy, 0, 8, st));
-    k_combine<CF><<<(2 * n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, acc_n, L,
+    k_combine<CF><<<(n_chunks + 127) / 128, 128, 0, st>>>(acc_keys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, acc_n, L,
                                                              ctx->buckets.p, d_heavy, heavy_cap);
     k_combine_heavy<CF, 32><<<148 * 2, HV_THREADS, 0, st>>>(acc_keys, (const uint32_t*)ctx->part_keys.p, ctx->part_pts.p, acc_n, L,
                                                            ctx->buckets.p, d_heavy, heavy_cap);
