@@ -192,7 +192,7 @@ int mira_msm_set_pipeline(mira_msm_ctx *ctx, int slices, size_t min_scalars_per_
  * entries 2k and 2k+1 of its own chunk in affine coordinates (one inversion per thread, mira_b200/csrc/inv30.cuh) and
  * feeds the sums to the XYZZ accumulation (k_pair_up / k_pair_add / k_pair_acc).  Measured slower on B200 (36.8 ms
  * against 31.8 ms of accumulation at 2^24 points: bound by the second gather of the table points). */
-#define MIRA_AFFINE_THREAD_LOCAL_PAIRS (-2)
+enum { MIRA_AFFINE_THREAD_LOCAL_PAIRS = -2 };
 int mira_msm_set_affine_levels(mira_msm_ctx *ctx, int levels);
 
 /* ==== field vectors in HBM: the witness side of the hot path =====
