@@ -53,32 +53,32 @@ struct Coop {
     const bool acc_id = xyzz_is_identity(acc), q_id = xyzz_is_identity(q);
     Fe<CF> mine = fe_zero<CF>(), u1, u2, s1, s2;
     // stage A: u1 = x1*zz2, u2 = x2*zz1, s1 = y1*zzz2, s2 = y2*zzz1
-    if (warp == 0) mine = fe_mul(acc.x, q.zz);
-    else if (warp == 1) mine = fe_mul(q.x, acc.zz);
-    else if (warp == 2) mine = fe_mul(acc.y, q.zzz);
-    else mine = fe_mul(q.y, acc.zzz);
+    if (warp == 0) mine = fe_mulc(acc.x, q.zz);
+    else if (warp == 1) mine = fe_mulc(q.x, acc.zz);
+    else if (warp == 2) mine = fe_mulc(acc.y, q.zzz);
+    else mine = fe_mulc(q.y, acc.zzz);
     exchange(mine, u1, u2, s1, s2);
     const Fe<CF> p = fe_sub(u2, u1), r = fe_sub(s2, s1);
     const bool same_x = !acc_id && !q_id && fe_is_zero(p);      // doubling or cancellation: rare, handled below
     // stage B: pp = p^2, rr = r^2, zzm = zz1*zz2, zzzm = zzz1*zzz2
     Fe<CF> pp, rr, zzm, zzzm;
-    if (warp == 0) mine = fe_sqr(p);
-    else if (warp == 1) mine = fe_sqr(r);
-    else if (warp == 2) mine = fe_mul(acc.zz, q.zz);
-    else mine = fe_mul(acc.zzz, q.zzz);
+    if (warp == 0) mine = fe_sqrc(p);
+    else if (warp == 1) mine = fe_sqrc(r);
+    else if (warp == 2) mine = fe_mulc(acc.zz, q.zz);
+    else mine = fe_mulc(acc.zzz, q.zzz);
     exchange(mine, pp, rr, zzm, zzzm);
     // stage C: ppp = p*pp, qq = u1*pp, zz3 = zzm*pp
     Fe<CF> ppp, qq, zz3, unused;
-    if (warp == 0) mine = fe_mul(p, pp);
-    else if (warp == 1) mine = fe_mul(u1, pp);
-    else if (warp == 2) mine = fe_mul(zzm, pp);
+    if (warp == 0) mine = fe_mulc(p, pp);
+    else if (warp == 1) mine = fe_mulc(u1, pp);
+    else if (warp == 2) mine = fe_mulc(zzm, pp);
     exchange(mine, ppp, qq, zz3, unused);
     const Fe<CF> x3 = fe_sub(fe_sub(rr, ppp), fe_dbl(qq));
     // stage D: t1 = r*(qq - x3), t2 = s1*ppp, zzz3 = zzzm*ppp
     Fe<CF> t1, t2, zzz3;
-    if (warp == 0) mine = fe_mul(r, fe_sub(qq, x3));
-    else if (warp == 1) mine = fe_mul(s1, ppp);
-    else if (warp == 2) mine = fe_mul(zzzm, ppp);
+    if (warp == 0) mine = fe_mulc(r, fe_sub(qq, x3));
+    else if (warp == 1) mine = fe_mulc(s1, ppp);
+    else if (warp == 2) mine = fe_mulc(zzzm, ppp);
     exchange(mine, t1, t2, zzz3, unused);
     Xyzz<CF> out;
     out.x = x3;
@@ -104,23 +104,23 @@ struct Coop {
     const Fe<CF> u = fe_dbl(p.y);
     Fe<CF> mine = fe_zero<CF>(), v, xx, unused, unused2;
     // stage A: v = u^2, xx = x^2
-    if (warp == 0) mine = fe_sqr(u);
-    else if (warp == 1) mine = fe_sqr(p.x);
+    if (warp == 0) mine = fe_sqrc(u);
+    else if (warp == 1) mine = fe_sqrc(p.x);
     exchange(mine, v, xx, unused, unused2);
     const Fe<CF> m = fe_add(fe_dbl(xx), xx);
     // stage B: w = u*v, s = x*v, zz3 = v*zz, mm = m^2
     Fe<CF> w, s, zz3, mm;
-    if (warp == 0) mine = fe_mul(u, v);
-    else if (warp == 1) mine = fe_mul(p.x, v);
-    else if (warp == 2) mine = fe_mul(v, p.zz);
-    else mine = fe_sqr(m);
+    if (warp == 0) mine = fe_mulc(u, v);
+    else if (warp == 1) mine = fe_mulc(p.x, v);
+    else if (warp == 2) mine = fe_mulc(v, p.zz);
+    else mine = fe_sqrc(m);
     exchange(mine, w, s, zz3, mm);
     const Fe<CF> x3 = fe_sub(mm, fe_dbl(s));
     // stage C: t1 = m*(s - x3), t2 = w*y, zzz3 = w*zzz
     Fe<CF> t1, t2, zzz3;
-    if (warp == 0) mine = fe_mul(m, fe_sub(s, x3));
-    else if (warp == 1) mine = fe_mul(w, p.y);
-    else if (warp == 2) mine = fe_mul(w, p.zzz);
+    if (warp == 0) mine = fe_mulc(m, fe_sub(s, x3));
+    else if (warp == 1) mine = fe_mulc(w, p.y);
+    else if (warp == 2) mine = fe_mulc(w, p.zzz);
     exchange(mine, t1, t2, zzz3, unused);
     Xyzz<CF> out;
     out.x = x3;

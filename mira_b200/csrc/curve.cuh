@@ -97,14 +97,14 @@ template <class F> __device__ __noinline__ Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {
   Xyzz<F> r;
   Fe<F> u = fe_dbl(p.y);
   Fe<F> v = fe_sqr(u);
-  Fe<F> w = fe_mul(u, v);
-  Fe<F> s = fe_mul(p.x, v);
+  Fe<F> w = fe_mulc(u, v);
+  Fe<F> s = fe_mulc(p.x, v);
   Fe<F> xx = fe_sqr(p.x);
   Fe<F> m = fe_add(fe_dbl(xx), xx);
   r.x = fe_sub(fe_sqr(m), fe_dbl(s));
-  r.y = fe_sub(fe_mul(m, fe_sub(s, r.x)), fe_mul(w, p.y));
-  r.zz = fe_mul(v, p.zz);
-  r.zzz = fe_mul(w, p.zzz);
+  r.y = fe_sub(fe_mulc(m, fe_sub(s, r.x)), fe_mulc(w, p.y));
+  r.zz = fe_mulc(v, p.zz);
+  r.zzz = fe_mulc(w, p.zzz);
   return r;
 }
 
@@ -139,10 +139,10 @@ template <class F> __device__ __forceinline__ void xyzz_madd(Xyzz<F>& acc, const
 template <class F> __device__ __forceinline__ void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {
   if (xyzz_is_identity(q)) return;
   if (xyzz_is_identity(acc)) { acc = q; return; }
-  Fe<F> u1 = fe_mul(acc.x, q.zz);
-  Fe<F> u2 = fe_mul(q.x, acc.zz);
-  Fe<F> s1 = fe_mul(acc.y, q.zzz);
-  Fe<F> s2 = fe_mul(q.y, acc.zzz);
+  Fe<F> u1 = fe_mulc(acc.x, q.zz);
+  Fe<F> u2 = fe_mulc(q.x, acc.zz);
+  Fe<F> s1 = fe_mulc(acc.y, q.zzz);
+  Fe<F> s2 = fe_mulc(q.y, acc.zzz);
   Fe<F> p = fe_sub(u2, u1);
   Fe<F> r = fe_sub(s2, s1);
   if (fe_is_zero(p)) {
@@ -151,14 +151,14 @@ template <class F> __device__ __forceinline__ void xyzz_add(Xyzz<F>& acc, const 
     return;
   }
   Fe<F> pp = fe_sqr(p);
-  Fe<F> ppp = fe_mul(p, pp);
-  Fe<F> qq = fe_mul(u1, pp);
+  Fe<F> ppp = fe_mulc(p, pp);
+  Fe<F> qq = fe_mulc(u1, pp);
   Fe<F> x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
   Fe<F> y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
-  acc.zz = fe_mul(fe_mul(acc.zz, q.zz), pp);
-  acc.zzz = fe_mul(fe_mul(acc.zzz, q.zzz), ppp);
+  acc.zz = fe_mulc(fe_mulc(acc.zz, q.zz), pp);
+  acc.zzz = fe_mulc(fe_mulc(acc.zzz, q.zzz), ppp);
 }
 
 // Curve::to_affine: identity -> (0, 0); one inversion.
