@@ -96,12 +96,12 @@ template <class F> __device__ __noinline__ Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {
   if (xyzz_is_identity(p) || fe_is_zero(p.y)) return xyzz_identity<F>();
   Xyzz<F> r;
   Fe<F> u = fe_dbl(p.y);
-  Fe<F> v = fe_sqr(u);
+  Fe<F> v = fe_sqrc(u);
   Fe<F> w = fe_mulc(u, v);
   Fe<F> s = fe_mulc(p.x, v);
-  Fe<F> xx = fe_sqr(p.x);
+  Fe<F> xx = fe_sqrc(p.x);
   Fe<F> m = fe_add(fe_dbl(xx), xx);
-  r.x = fe_sub(fe_sqr(m), fe_dbl(s));
+  r.x = fe_sub(fe_sqrc(m), fe_dbl(s));
   r.y = fe_sub(fe_mulc(m, fe_sub(s, r.x)), fe_mulc(w, p.y));
   r.zz = fe_mulc(v, p.zz);
   r.zzz = fe_mulc(w, p.zzz);
@@ -150,11 +150,11 @@ template <class F> __device__ __forceinline__ void xyzz_add(Xyzz<F>& acc, const 
     else acc = xyzz_identity<F>();
     return;
   }
-  Fe<F> pp = fe_sqr(p);
+  Fe<F> pp = fe_sqrc(p);
   Fe<F> ppp = fe_mulc(p, pp);
   Fe<F> qq = fe_mulc(u1, pp);
-  Fe<F> x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fe<F> y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), s1, ppp);
+  Fe<F> x3 = fe_sub(fe_sub(fe_sqrc(r), ppp), fe_dbl(qq));
+  Fe<F> y3 = fe_mul_sub_mulc(r, fe_sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fe_mulc(fe_mulc(acc.zz, q.zz), pp);

@@ -166,6 +166,11 @@ template <class F> __device__ __forceinline__ Fe<F> fe_mul_sub_mul(const Fe<F>& 
   return fe_sub(fe_mul(a, b), fe_mul(c, d));
 #endif
 }
+// ... and out of line, for xyzz_add / xyzz_dbl (see fe_mul_call)
+template <class F> __device__ __noinline__ Fe<F> fe_mul_sub_mul_call(Fe<F> a, Fe<F> b, Fe<F> c, Fe<F> d) { return fe_mul_sub_mul(a, b, c, d); }
+template <class F> __device__ __forceinline__ Fe<F> fe_mul_sub_mulc(const Fe<F>& a, const Fe<F>& b, const Fe<F>& c, const Fe<F>& d) {
+  return fe_mul_sub_mul_call<F>(a, b, c, d);
+}
 template <class F> __device__ __forceinline__ Fe<F> fe_add(const Fe<F>& a, const Fe<F>& b) {
   Fe<F> r;
   mod_add_raw(F{}, r.v, a.v, b.v);
