@@ -9,6 +9,11 @@
 #pragma once
 #include "field.cuh"
 
+// 1 (shipped): three products of the mixed addition are called out of line (xyzz_madd below); 0: all inlined
+#ifndef MIRA_MADD_CALLS
+#define MIRA_MADD_CALLS 1
+#endif
+
 namespace mira {
 
 // Affine point as the reference stores it: {x, y}, 64 bytes, identity = (0, 0).
@@ -109,6 +114,10 @@ template <class F> __device__ __noinline__ Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {
 }
 
 // acc += q (q affine, possibly negated by the caller).  madd-2008-s.
+// Three of its ten products (Q = X1*PP and the two ZZ updates) are called out of line: k_accumulate's loop body shrinks
+// from 37 KB to 26 KB and fetch stalls less, while the products ptxas overlaps with their neighbours stay inlined.
+// Measured at 2^24 points, accumulation phase (ms): all inlined 31.66 | ZZ, ZZZ 31.44 | + Q 31.35 | U2, S2, ZZ, ZZZ 31.48 |
+// PPP, Q, ZZ, ZZZ 31.48 | all six plain products 32.31.  MIRA_MADD_CALLS=0 restores the fully inlined form.
 template <class F> __device__ __forceinline__ void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q) {
   if (aff_is_identity(q)) return;
   if (xyzz_is_identity(acc)) {
@@ -126,13 +135,22 @@ template <class F> __device__ __forceinline__ void xyzz_madd(Xyzz<F>& acc, const
   }
   Fe<F> pp = fe_sqr(p);
   Fe<F> ppp = fe_mul(p, pp);
+#if MIRA_MADD_CALLS
+  Fe<F> qq = fe_mulc(acc.x, pp);
+#else
   Fe<F> qq = fe_mul(acc.x, pp);
+#endif
   Fe<F> x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
   Fe<F> y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
+#if MIRA_MADD_CALLS
+  acc.zz = fe_mulc(acc.zz, pp);
+  acc.zzz = fe_mulc(acc.zzz, ppp);
+#else
   acc.zz = fe_mul(acc.zz, pp);
   acc.zzz = fe_mul(acc.zzz, ppp);
+#endif
 }
 
 // acc += q (both XYZZ).  add-2008-s.

@@ -119,8 +119,8 @@ template <class F> __device__ __forceinline__ Fe<F> fe_mul(const Fe<F>& a, const
 // operations of the reduction and stitching kernels (xyzz_add, xyzz_dbl: 14 / 9 products each, inlined several times
 // per kernel) use it: those kernels run a few hundred warps on long dependent chains, their bodies were 100+ KB of
 // straight-line code, and instruction fetch was what they waited for (bucket reduction 1.76 -> 1.59 ms at 2^21 buckets,
-// 0.32 -> 0.25 ms at 2^16).  k_accumulate keeps the inlined product: called out of line it is 2 % SLOWER (32.3 against
-// 31.7 ms; ptxas no longer overlaps neighbouring products).
+// 0.32 -> 0.25 ms at 2^16).  k_accumulate calls three of the mixed addition's ten products this way (curve.cuh); with all
+// of them out of line it is 2 % SLOWER (32.3 against 31.7 ms: ptxas no longer overlaps neighbouring products).
 template <class F> __device__ __noinline__ Fe<F> fe_mul_call(Fe<F> a, Fe<F> b) {
   Fe<F> r;
   mont_mul_raw(F{}, r.v, a.v, b.v);
