@@ -118,14 +118,18 @@ template <class F> __device__ __noinline__ Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {
 // from 37 KB to 26 KB and fetch stalls less, while the products ptxas overlaps with their neighbours stay inlined.
 // Measured at 2^24 points, accumulation phase (ms): all inlined 31.66 | ZZ, ZZZ 31.44 | + Q 31.35 | U2, S2, ZZ, ZZZ 31.48 |
 // PPP, Q, ZZ, ZZZ 31.48 | all six plain products 32.31.  MIRA_MADD_CALLS=0 restores the fully inlined form.
+#ifndef MIRA_MADD_MASK
+#define MIRA_MADD_MASK (MIRA_MADD_CALLS ? 400 : 0)      // bit k: product k of the list below goes out of line
+#endif
+#define MIRA_MM(bit, inl, call) ((MIRA_MADD_MASK & (bit)) ? (call) : (inl))
 template <class F> __device__ __forceinline__ void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q) {
   if (aff_is_identity(q)) return;
   if (xyzz_is_identity(acc)) {
     acc.x = q.x; acc.y = q.y; acc.zz = fe_one<F>(); acc.zzz = fe_one<F>();
     return;
   }
-  Fe<F> u2 = fe_mul(q.x, acc.zz);
-  Fe<F> s2 = fe_mul(q.y, acc.zzz);
+  Fe<F> u2 = MIRA_MM(1, fe_mul(q.x, acc.zz), fe_mulc(q.x, acc.zz));
+  Fe<F> s2 = MIRA_MM(2, fe_mul(q.y, acc.zzz), fe_mulc(q.y, acc.zzz));
   Fe<F> p = fe_sub(u2, acc.x);
   Fe<F> r = fe_sub(s2, acc.y);
   if (fe_is_zero(p)) {                       // same x: doubling or cancellation (rare)
@@ -133,24 +137,16 @@ template <class F> __device__ __forceinline__ void xyzz_madd(Xyzz<F>& acc, const
     else acc = xyzz_identity<F>();
     return;
   }
-  Fe<F> pp = fe_sqr(p);
-  Fe<F> ppp = fe_mul(p, pp);
-#if MIRA_MADD_CALLS
-  Fe<F> qq = fe_mulc(acc.x, pp);
-#else
-  Fe<F> qq = fe_mul(acc.x, pp);
-#endif
-  Fe<F> x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fe<F> y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), acc.y, ppp);
+  Fe<F> pp = MIRA_MM(4, fe_sqr(p), fe_sqrc(p));
+  Fe<F> ppp = MIRA_MM(8, fe_mul(p, pp), fe_mulc(p, pp));
+  Fe<F> qq = MIRA_MM(16, fe_mul(acc.x, pp), fe_mulc(acc.x, pp));
+  Fe<F> rr = MIRA_MM(32, fe_sqr(r), fe_sqrc(r));
+  Fe<F> x3 = fe_sub(fe_sub(rr, ppp), fe_dbl(qq));
+  Fe<F> y3 = MIRA_MM(64, fe_mul_sub_mul(r, fe_sub(qq, x3), acc.y, ppp), fe_mul_sub_mulc(r, fe_sub(qq, x3), acc.y, ppp));
   acc.x = x3;
   acc.y = y3;
-#if MIRA_MADD_CALLS
-  acc.zz = fe_mulc(acc.zz, pp);
-  acc.zzz = fe_mulc(acc.zzz, ppp);
-#else
-  acc.zz = fe_mul(acc.zz, pp);
-  acc.zzz = fe_mul(acc.zzz, ppp);
-#endif
+  acc.zz = MIRA_MM(128, fe_mul(acc.zz, pp), fe_mulc(acc.zz, pp));
+  acc.zzz = MIRA_MM(256, fe_mul(acc.zzz, ppp), fe_mulc(acc.zzz, ppp));
 }
 
 // acc += q (both XYZZ).  add-2008-s.
