@@ -402,12 +402,12 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
       CU(cudaGetLastError());
       in_b = 1;
     } else {
-    // ---- the remaining passes (bit 8 up) of the LSD radix sort, from the s-buffers into the plain ones and back
-    int in_plain = 0;
-    if ((rc = radix_sort_pairs((uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, (uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, d_npairs, E_sort,
-                               key_bits, sb.tile_sums.p, st, &in_plain, &plan->launches, 1)))
-      return rc;
-    in_b = !in_plain;
+      // ---- the remaining passes (bit 8 up) of the LSD radix sort, from the s-buffers into the plain ones and back
+      int in_plain = 0;
+      if ((rc = radix_sort_pairs((uint32_t*)sb.skeys.p, (uint32_t*)sb.srefs.p, (uint32_t*)sb.keys.p, (uint32_t*)sb.refs.p, d_npairs,
+                                 E_sort, key_bits, sb.tile_sums.p, st, &in_plain, &plan->launches, 1)))
+        return rc;
+      in_b = !in_plain;
     }
   } else {
     if (pt) pt->mark(1);
