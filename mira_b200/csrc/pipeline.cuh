@@ -660,14 +660,18 @@ inline int reduce_level_log_m(uint32_t n, int levels_done, unsigned n_sets) {
   static const int min_n_log = [] { const char* e = getenv("MIRA_RED_MIN_N_LOG"); return e ? atoi(e) : 14; }();
   static const int batch_log_m = [] { const char* e = getenv("MIRA_RED_LOG_M"); return e ? atoi(e) : 0; }();
   if (levels_done == 0) {
-    if (n_sets == 1) return n >= ((uint32_t)1 << 20) ? 4 : 0;
+    // single commits: MIRA_RED1_MIN_LOG / MIRA_RED1_LOG_M / MIRA_RED1_NEXT_MIN_LOG move the thresholds (sweeps)
+    static const int one_min_log = [] { const char* e = getenv("MIRA_RED1_MIN_LOG"); return e ? atoi(e) : 20; }();
+    static const int one_log_m = [] { const char* e = getenv("MIRA_RED1_LOG_M"); return e ? atoi(e) : 4; }();
+    if (n_sets == 1) return n >= ((uint32_t)1 << one_min_log) ? one_log_m : 0;
     // batched commits (profiles/r02_reduce_levels.txt): 6 x 2^19 points (c = 17) 11.39 -> 9.78 ms, 6 x 2^16 (c = 15)
     // 2.29 -> 2.09 ms with chunks of 8 (2.18 with 16; the larger sets prefer 16: 9.80 against 9.90); below 2^17 buckets in
     // all the cooperative kernels (coop.cuh) are a little faster still (6 x 2^16 points: 2.04 ms)
     if ((uint64_t)n * n_sets < ((uint64_t)1 << min_log) || n < ((uint32_t)1 << min_n_log)) return 0;
     return batch_log_m ? batch_log_m : (n < ((uint32_t)1 << 15) ? 3 : 4);
   }
-  return n >= ((uint32_t)1 << 13) ? 4 : 0;
+  static const int next_min_log = [] { const char* e = getenv("MIRA_RED1_NEXT_MIN_LOG"); return e ? atoi(e) : 13; }();
+  return n >= ((uint32_t)1 << next_min_log) ? 4 : 0;
 }
 
 template <class CF>
