@@ -2,9 +2,12 @@
 //
 // Replaces halo2_proofs::arithmetic::best_multiexp as called from CommitmentKey::commit
 // (/root/reference/src/commitment.rs:78-87).  Pipeline:
-//   k_digits      scalar: Montgomery -> canonical, signed c-bit digits, (bucket, point-ref) pairs
-//   sort          group the pairs by bucket (sort.cu: LSD radix sort staged through shared memory)
-//   k_accumulate  load-balanced segmented XYZZ mixed-add over the sorted list (fixed-size chunks)
+//   digits        scalar: Montgomery -> canonical, signed c-bit digits, (bucket, point-ref) pairs.  k_digit_hist +
+//                 k_digits_scatter place the pairs straight into 256 bins (the sort's first pass, fused); sparse
+//                 vectors keep k_digits' compacted list
+//   grouping      pairs of one bucket made contiguous: the MSD partition k_msd_* below (from 2^25 pairs), else the
+//                 stable LSD passes of sort.cu
+//   k_accumulate  load-balanced segmented XYZZ mixed-add over the grouped list (fixed-size chunks)
 //   k_combine     stitch runs that straddle chunk boundaries
 //   k_reduce_*    S = sum_b b * bucket[b] by chunked running sums + tree sum
 //   k_finalize    to_affine
