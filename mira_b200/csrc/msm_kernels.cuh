@@ -457,14 +457,15 @@ static __global__ void __launch_bounds__(MSD_M_THREADS) k_msd_mid(const uint32_t
 
 // Block b sorts groups [b * gpb, (b + 1) * gpb) by the key's low `low_bits` (1..8) bits.  A range
 // of up to MSD_LOW_CAP pairs is ranked from registers, re-ordered in shared memory and written back in order (coalesced);
-// a larger one (skewed vectors) goes through two passes over global memory: histogram, then placement.
+// a larger one is histogrammed first and then takes the same steps MSD_LOW_CAP pairs at a time.
 #ifndef MIRA_MSD_L_ITEMS
 #define MIRA_MSD_L_ITEMS 16
 #endif
 constexpr int MSD_L_THREADS = 256;
 constexpr int MSD_LOW_ITEMS = MIRA_MSD_L_ITEMS;
 constexpr int MSD_LOW_CAP = MSD_L_THREADS * MSD_LOW_ITEMS;      // 4096 pairs, 32 KiB
-constexpr int MSD_LOW_MAX_AVG = 3400;                           // the host uses the MSD path while pairs / groups stays below this
+constexpr int MSD_LOW_MAX_AVG = 3400;                           // groups average at most this for the one-chunk path to be the common case
+constexpr int MSD_LOW_MAX_AVG_CHUNKED = 12000;                  // ... and this with the chunked path (a 2^26-point commit: 11,264)
 
 static __global__ void __launch_bounds__(MSD_L_THREADS) k_msd_low(const uint32_t* __restrict__ in_keys, const uint32_t* __restrict__ in_refs,
                                                                   const uint32_t* __restrict__ offs16, uint32_t gpb, int low_bits,
@@ -517,18 +518,54 @@ static __global__ void __launch_bounds__(MSD_L_THREADS) k_msd_low(const uint32_t
       }
       __syncthreads();
     } else {
+      // oversized range (a 2^25..2^26-point commit, the top window's heavy buckets, skewed vectors): histogram of the
+      // whole range, then MSD_LOW_CAP pairs at a time through the same rank / re-order / write-in-runs steps, every bin's
+      // write position carried from chunk to chunk
+      __shared__ uint32_t pos[256], cstart[256];
       for (uint32_t i = lo + threadIdx.x; i < hi; i += MSD_L_THREADS) atomicAdd(&cnt[(__ldg(in_keys + i) - 1u) & mask], 1u);
       __syncthreads();
       const uint32_t ex = ds_scan256(cnt[threadIdx.x], tmp, total);
-      cnt[threadIdx.x] = lo + ex;                    // next free slot of every low value
-      __syncthreads();
-      for (uint32_t i = lo + threadIdx.x; i < hi; i += MSD_L_THREADS) {
-        const uint32_t k = __ldg(in_keys + i);
-        const uint32_t dst = atomicAdd(&cnt[(k - 1u) & mask], 1u);
-        out_keys[dst] = k;
-        out_refs[dst] = __ldg(in_refs + i);
+      pos[threadIdx.x] = lo + ex;
+      for (uint32_t base = lo; base < hi; base += MSD_LOW_CAP) {
+        const uint32_t top = base + MSD_LOW_CAP < hi ? base + MSD_LOW_CAP : hi;
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t key[MSD_LOW_ITEMS], ref[MSD_LOW_ITEMS], rank[MSD_LOW_ITEMS];
+#pragma unroll
+        for (int k = 0; k < MSD_LOW_ITEMS; k++) {
+          const uint32_t i = base + k * MSD_L_THREADS + threadIdx.x;
+          key[k] = i < top ? __ldg(in_keys + i) : 0u;
+          ref[k] = i < top ? __ldg(in_refs + i) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < MSD_LOW_ITEMS; k++) {
+          const uint32_t i = base + k * MSD_L_THREADS + threadIdx.x;
+          if (i < top) rank[k] = atomicAdd(&cnt[(key[k] - 1u) & mask], 1u);
+        }
+        __syncthreads();
+        const uint32_t mine = cnt[threadIdx.x];
+        cstart[threadIdx.x] = ds_scan256(mine, tmp, total);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < MSD_LOW_ITEMS; k++) {
+          const uint32_t i = base + k * MSD_L_THREADS + threadIdx.x;
+          if (i < top) {
+            const uint32_t q = cstart[(key[k] - 1u) & mask] + rank[k];
+            st_keys[q] = key[k];
+            st_refs[q] = ref[k];
+          }
+        }
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < top - base; q += MSD_L_THREADS) {
+          const uint32_t kk = st_keys[q];
+          const uint32_t b = (kk - 1u) & mask;
+          const uint32_t dst = pos[b] + (q - cstart[b]);
+          out_keys[dst] = kk;
+          out_refs[dst] = st_refs[q];
+        }
+        __syncthreads();
+        pos[threadIdx.x] += mine;                    // thread t owns bin t
       }
-      __syncthreads();
     }
   }
 }

@@ -323,7 +323,7 @@ int msm_prep(mira_msm_ctx* ctx, MsmPlan* plan, const void* const* d_scalar_sets,
   int msd_bits = 1;          // the MSD partition works on key - 1 < n_sets * (B + 1) - 1 (a single set: c - 1 bits, evenly filled)
   while (((uint64_t)1 << msd_bits) < (uint64_t)plan->n_sets * (plan->B + 1) - 1) msd_bits++;
   const bool msd_on = fused_on && msd_env && !plan->heavy && msd_bits >= MSD_GROUP_BITS + 1 && msd_bits <= MSD_GROUP_BITS + 8 && E >= msd_min_pairs &&
-                      (E >> MSD_GROUP_BITS) <= (size_t)MSD_LOW_MAX_AVG;
+                      (E >> MSD_GROUP_BITS) <= (size_t)MSD_LOW_MAX_AVG_CHUNKED;
   const int low_bits = msd_bits - MSD_GROUP_BITS;
   uint32_t* d_offs1 = (uint32_t*)((char*)sb.counts.p + 4096);                 // [257] segment starts
   uint32_t* d_tile_tab = d_offs1 + 320;                                       // [257]
