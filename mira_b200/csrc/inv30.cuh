@@ -1,6 +1,6 @@
 // inv30.cuh — modular inversion by batched division steps ("safegcd", Bernstein & Yang 2019) on signed 30-bit limbs.
 //
-// Used where every lane of a warp inverts at once (the thread-local pair pre-addition of k_accumulate_pair, the
+// Used where every lane of a warp inverts at once (the thread-local pair pre-addition of k_pair_up, the
 // fixed-base table build): the control flow is the same for every input, and the cost is ~14,000 instructions per
 // inversion instead of the ~115,000 of the bit-by-bit binary GCD (fe_inv_uniform in field.cuh works on four
 // 256-bit numbers per bit; this works on two 32-bit words per bit and touches the long numbers once per 30 bits).
