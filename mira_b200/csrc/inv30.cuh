@@ -2,8 +2,9 @@
 //
 // Used where every lane of a warp inverts at once (the thread-local pair pre-addition of k_pair_up, the
 // fixed-base table build): the control flow is the same for every input, and the cost is ~14,000 instructions per
-// inversion instead of the ~115,000 of the bit-by-bit binary GCD (fe_inv_uniform in field.cuh works on four
-// 256-bit numbers per bit; this works on two 32-bit words per bit and touches the long numbers once per 30 bits).
+// inversion instead of the ~115,000 of round 1's bit-by-bit uniform binary GCD (which worked on four 256-bit numbers
+// per bit; this works on two 32-bit words per bit and touches the long numbers once per 30 bits).  It is what
+// fe_inv_uniform (field.cuh) runs.
 //
 // The algorithm is the published one (a divstep maps (delta, f, g) with f odd to (1 - delta, g, (g - f) / 2) if
 // delta > 0 and g is odd, and to (1 + delta, f, (g + (g odd) f) / 2) otherwise; 590 steps bring any 256-bit g to 0
